@@ -1,0 +1,494 @@
+// TEST INFRASTRUCTURE ONLY -- a CPU restatement of the reference algorithm.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+// load this library; the product (blockcg_b200/) never does.
+//
+// Parity status: PINNED.  Every function below is checked in
+// tests/test_oracle.py against (a) the committed golden fixtures under
+// tests/golden/ that were generated from the unmodified reference
+// (oracle/gen_golden.py -> oracle/_ref/libref_n<N>.so) and (b), when
+// oracle/_ref is present, live outputs of the reference on fresh inputs.
+//
+// Plain loops over (re,im) doubles; no Eigen.  Layouts are the reference's:
+//   field  [V][N][3] complex128 (inc/fields.hpp:18-30, 3xN column-major/site)
+//   links  [V][3][3] complex128 column-major (inc/dirac_op.hpp:10-11)
+//   matrix NxN complex128 column-major (inc/fields.hpp:22-23)
+// Citations are relative to /root/reference.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+using cd = std::complex<double>;
+using cvec = std::vector<cd>;
+
+inline const cd* C(const double* p) { return reinterpret_cast<const cd*>(p); }
+inline cd* C(double* p) { return reinterpret_cast<cd*>(p); }
+
+// element (colour c, rhs r) of site x
+inline size_t fidx(int N, int x, int r, int c) { return (static_cast<size_t>(x) * N + r) * 3 + c; }
+// element (i,j) of link x, column-major
+inline size_t uidx(int x, int i, int j) { return static_cast<size_t>(x) * 9 + i + 3 * j; }
+// element (i,j) of an NxN column-major matrix
+inline size_t midx(int N, int i, int j) { return i + static_cast<size_t>(N) * j; }
+
+double now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// inc/dirac_op.hpp:14-21  lhs[x] = 0.5 U[x] rhs[x+1] - 0.5 U[x-1]^dag rhs[x-1], periodic
+void D(int V, int N, const cd* U, const cd* in, cd* out) {
+  for (int x = 0; x < V; ++x) {
+    int xp = (x + 1) % V, xm = (x - 1 + V) % V;
+    for (int r = 0; r < N; ++r)
+      for (int i = 0; i < 3; ++i) {
+        cd a = 0, b = 0;
+        for (int j = 0; j < 3; ++j) {
+          a += (0.5 * U[uidx(x, i, j)]) * in[fidx(N, xp, r, j)];
+          b += (0.5 * std::conj(U[uidx(xm, j, i)])) * in[fidx(N, xm, r, j)];
+        }
+        out[fidx(N, x, r, i)] = a - b;
+      }
+  }
+}
+
+// inc/dirac_op.hpp:36-43  lhs = m^2 rhs - D(D(rhs));  (+ sigma*rhs: block_solvers.hpp:136)
+void op(int V, int N, double mass, const cd* U, const cd* in, cd* out, double sigma) {
+  cvec tmp(static_cast<size_t>(V) * N * 3);
+  D(V, N, U, in, tmp.data());
+  D(V, N, U, tmp.data(), out);
+  const size_t n = static_cast<size_t>(V) * N * 3;
+  const double m2 = mass * mass;
+  for (size_t k = 0; k < n; ++k) {
+    cd t = out[k] * (-1.0);  // rescale_add(-1.0, rhs, m^2): fields.hpp:85-86
+    t += in[k] * m2;
+    out[k] = t;
+  }
+  if (sigma != 0.0)
+    for (size_t k = 0; k < n; ++k) out[k] += in[k] * sigma;
+}
+
+// one site's contribution to the lower triangle: fields.hpp:109-113
+inline void gram_site(int N, const cd* a, const cd* b, int x, cd* R) {
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j <= i; ++j) {
+      cd s = 0;
+      for (int c = 0; c < 3; ++c) s += std::conj(a[fidx(N, x, i, c)]) * b[fidx(N, x, j, c)];
+      R[midx(N, i, j)] += s;
+    }
+}
+
+// inc/fields.hpp:103-122.  chunk<=0: the reference's strictly sequential
+// accumulation over sites.  chunk>0: sequential partial sums over blocks of
+// `chunk` consecutive sites combined by a fixed pairwise tree (the summation
+// shape of a parallel reduction) -- used to separate "Gram
+// rounding" from "algorithm" when iteration counts are compared.
+void hermitian_dot(int V, int N, const cd* a, const cd* b, cd* R, int chunk) {
+  const size_t nn = static_cast<size_t>(N) * N;
+  std::fill(R, R + nn, cd(0));
+  if (chunk <= 0) {
+    for (int x = 0; x < V; ++x) gram_site(N, a, b, x, R);
+  } else {
+    int nch = (V + chunk - 1) / chunk;
+    cvec part(static_cast<size_t>(nch) * nn, cd(0));
+    for (int c = 0; c < nch; ++c)
+      for (int x = c * chunk; x < std::min(V, (c + 1) * chunk); ++x) gram_site(N, a, b, x, &part[c * nn]);
+    for (int stride = 1; stride < nch; stride *= 2)
+      for (int c = 0; c + stride < nch; c += 2 * stride)
+        for (size_t k = 0; k < nn; ++k) part[c * nn + k] += part[(c + stride) * nn + k];
+    std::copy(part.begin(), part.begin() + nn, R);
+  }
+  for (int i = 1; i < N; ++i)
+    for (int j = 0; j < i; ++j) R[midx(N, j, i)] = std::conj(R[midx(N, i, j)]);
+}
+
+// inc/fields.hpp:70-77  this[x] += rhs[x] * M
+void add(int V, int N, cd* dst, const cd* src, const cd* M) {
+  for (int x = 0; x < V; ++x)
+    for (int j = 0; j < N; ++j)
+      for (int c = 0; c < 3; ++c) {
+        cd s = 0;
+        for (int k = 0; k < N; ++k) s += src[fidx(N, x, k, c)] * M[midx(N, k, j)];
+        dst[fidx(N, x, j, c)] += s;
+      }
+}
+
+void add_scalar(int V, int N, cd* dst, const cd* src, double s) {
+  const size_t n = static_cast<size_t>(V) * N * 3;
+  for (size_t k = 0; k < n; ++k) dst[k] += src[k] * s;
+}
+
+// inc/fields.hpp:79-90  this[x] = this[x]*L + rhs[x]*r
+void rescale_add(int V, int N, cd* dst, const cd* L, const cd* src, double r) {
+  cvec tmp(static_cast<size_t>(N) * 3);
+  for (int x = 0; x < V; ++x) {
+    for (int j = 0; j < N; ++j)
+      for (int c = 0; c < 3; ++c) {
+        cd s = 0;
+        for (int k = 0; k < N; ++k) s += dst[fidx(N, x, k, c)] * L[midx(N, k, j)];
+        s += src[fidx(N, x, j, c)] * r;
+        tmp[j * 3 + c] = s;
+      }
+    for (int k = 0; k < 3 * N; ++k) dst[static_cast<size_t>(x) * N * 3 + k] = tmp[k];
+  }
+}
+
+// inc/fields.hpp:125-136  column-wise back substitution, this <- this R^-1
+void trsm_upper_rhs(int V, int N, cd* q, const cd* R) {
+  for (int x = 0; x < V; ++x)
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < i; ++j)
+        for (int c = 0; c < 3; ++c) q[fidx(N, x, i, c)] -= R[midx(N, j, i)] * q[fidx(N, x, j, c)];
+      for (int c = 0; c < 3; ++c) q[fidx(N, x, i, c)] /= R[midx(N, i, i)];
+    }
+}
+
+// Eigen LLT lower, unblocked (Cholesky/LLT.h:301-328); returns the first
+// non-positive pivot column or -1.  Output R = L^dag (upper; zero below diag),
+// as fields.hpp:142 `.llt().matrixL().adjoint()`.
+// (For N>=32 Eigen switches to a blocked variant, LLT.h:330-360: same
+//  factor up to rounding.)
+int llt_upper(int N, const cd* A, cd* R) {
+  cvec L(A, A + static_cast<size_t>(N) * N);
+  int info = -1;
+  for (int k = 0; k < N; ++k) {
+    double x = L[midx(N, k, k)].real();
+    for (int j = 0; j < k; ++j) x -= std::norm(L[midx(N, k, j)]);
+    if (x <= 0.0) {
+      info = k;
+      break;
+    }
+    x = std::sqrt(x);
+    L[midx(N, k, k)] = x;
+    for (int i = k + 1; i < N; ++i) {
+      cd s = L[midx(N, i, k)];
+      for (int j = 0; j < k; ++j) s -= L[midx(N, i, j)] * std::conj(L[midx(N, k, j)]);
+      L[midx(N, i, k)] = s / x;
+    }
+  }
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) R[midx(N, i, j)] = (j >= i) ? std::conj(L[midx(N, j, i)]) : cd(0);
+  return info;
+}
+
+// Eigen FullPivLU compute + solve (LU/FullPivLU.h:487-590, 745-790, 317-341):
+// complete pivoting on |a_ij|, first maximum in column-major scan order,
+// rank threshold eps*N*|maxpivot| applied in the solve.
+void fullpivlu_solve(int N, const cd* A, const cd* B, int nb, cd* X) {
+  cvec lu(A, A + static_cast<size_t>(N) * N);
+  std::vector<int> rt(N), ct(N);
+  int nonzero = N;
+  double maxpivot = 0.0;
+  for (int k = 0; k < N; ++k) {
+    int br = k, bc = k;
+    double big = -1.0;
+    for (int j = k; j < N; ++j)
+      for (int i = k; i < N; ++i) {
+        double s = std::abs(lu[midx(N, i, j)]);
+        if (s > big) {
+          big = s;
+          br = i;
+          bc = j;
+        }
+      }
+    if (big == 0.0) {
+      nonzero = k;
+      for (int i = k; i < N; ++i) rt[i] = ct[i] = i;
+      break;
+    }
+    if (big > maxpivot) maxpivot = big;
+    rt[k] = br;
+    ct[k] = bc;
+    if (br != k)
+      for (int j = 0; j < N; ++j) std::swap(lu[midx(N, k, j)], lu[midx(N, br, j)]);
+    if (bc != k)
+      for (int i = 0; i < N; ++i) std::swap(lu[midx(N, i, k)], lu[midx(N, i, bc)]);
+    for (int i = k + 1; i < N; ++i) lu[midx(N, i, k)] /= lu[midx(N, k, k)];
+    for (int j = k + 1; j < N; ++j)
+      for (int i = k + 1; i < N; ++i) lu[midx(N, i, j)] -= lu[midx(N, i, k)] * lu[midx(N, k, j)];
+  }
+  // permutations: P from row transpositions applied in reverse, Q from column ones
+  std::vector<int> p(N), q(N);
+  for (int i = 0; i < N; ++i) p[i] = q[i] = i;
+  for (int k = N - 1; k >= 0; --k) std::swap(p[k], p[rt[k]]);
+  for (int k = 0; k < N; ++k) std::swap(q[k], q[ct[k]]);
+  // rank
+  const double thr = maxpivot * (2.220446049250313e-16 * N);
+  int rank = 0;
+  for (int i = 0; i < nonzero; ++i) rank += (std::abs(lu[midx(N, i, i)]) > thr);
+  if (rank == 0) {
+    std::fill(X, X + static_cast<size_t>(N) * nb, cd(0));
+    return;
+  }
+  // c = P * rhs : (P*rhs).row(p[i]) = rhs.row(i)
+  cvec c(static_cast<size_t>(N) * nb);
+  for (int col = 0; col < nb; ++col) {
+    cd* cc = &c[static_cast<size_t>(col) * N];
+    for (int i = 0; i < N; ++i) cc[p[i]] = B[midx(N, i, col)];
+    for (int i = 0; i < N; ++i)  // unit lower forward
+      for (int j = 0; j < i; ++j) cc[i] -= lu[midx(N, i, j)] * cc[j];
+    for (int i = rank - 1; i >= 0; --i) {  // upper backward on the leading rank block
+      for (int j = i + 1; j < rank; ++j) cc[i] -= lu[midx(N, i, j)] * cc[j];
+      cc[i] /= lu[midx(N, i, i)];
+    }
+    for (int i = 0; i < rank; ++i) X[midx(N, q[i], col)] = cc[i];
+    for (int i = rank; i < N; ++i) X[midx(N, q[i], col)] = 0;
+  }
+}
+
+void identity(int N, cd* I) {
+  std::fill(I, I + static_cast<size_t>(N) * N, cd(0));
+  for (int i = 0; i < N; ++i) I[midx(N, i, i)] = 1.0;
+}
+void fullpivlu_inverse(int N, const cd* A, cd* X) {
+  cvec I(static_cast<size_t>(N) * N);
+  identity(N, I.data());
+  fullpivlu_solve(N, A, I.data(), N, X);
+}
+
+// C = A*B (NxN)
+void mm(int N, const cd* A, const cd* B, cd* Cout) {
+  cvec t(static_cast<size_t>(N) * N);
+  for (int j = 0; j < N; ++j)
+    for (int i = 0; i < N; ++i) {
+      cd s = 0;
+      for (int k = 0; k < N; ++k) s += A[midx(N, i, k)] * B[midx(N, k, j)];
+      t[midx(N, i, j)] = s;
+    }
+  std::copy(t.begin(), t.end(), Cout);
+}
+void adjoint(int N, const cd* A, cd* out) {
+  cvec t(static_cast<size_t>(N) * N);
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) t[midx(N, i, j)] = std::conj(A[midx(N, j, i)]);
+  std::copy(t.begin(), t.end(), out);
+}
+// delta.rowwise().norm()  (block_solvers.hpp:61-62,130)
+void rownorms(int N, const cd* A, double* out) {
+  for (int i = 0; i < N; ++i) {
+    double s = 0;
+    for (int j = 0; j < N; ++j) s += std::norm(A[midx(N, i, j)]);
+    out[i] = std::sqrt(s);
+  }
+}
+
+void thinQR(int V, int N, cd* q, cd* R, int chunk) {
+  cvec G(static_cast<size_t>(N) * N);
+  hermitian_dot(V, N, q, q, G.data(), chunk);
+  llt_upper(N, G.data(), R);
+  trsm_upper_rhs(V, N, q, R);
+}
+
+}  // namespace
+
+extern "C" {
+
+// glibc rand() stream consumed exactly as benchmark.cpp:36-40 does through
+// Eigen's setRandom (Core/MathFunctions.h:618-628, 715-727): links first, then
+// B; each complex is (random<double>(), random<double>()) whose two calls gcc
+// evaluates right-to-left for this constructor, i.e. imag is drawn first.
+// (Checked bit-for-bit against ref_make_inputs in tests/test_oracle.py.)
+void ora_make_inputs(int V, int N, unsigned seed, double* U, double* B) {
+  std::srand(seed);
+  auto rnd = []() { return -1.0 + (1.0 - (-1.0)) * double(std::rand()) / double(RAND_MAX); };
+  auto fill = [&](double* p, size_t n) {
+    for (size_t k = 0; k < n; ++k) {
+      double im = rnd();
+      double re = rnd();
+      p[2 * k] = re;
+      p[2 * k + 1] = im;
+    }
+  };
+  fill(U, static_cast<size_t>(V) * 9);
+  fill(B, static_cast<size_t>(V) * N * 3);
+}
+
+void ora_op(int V, int N, double mass, const double* U, const double* in, double* out, double sigma) {
+  op(V, N, mass, C(U), C(in), C(out), sigma);
+}
+void ora_D(int V, int N, const double* U, const double* in, double* out) { D(V, N, C(U), C(in), C(out)); }
+void ora_hermitian_dot(int V, int N, const double* a, const double* b, double* R, int chunk) {
+  hermitian_dot(V, N, C(a), C(b), C(R), chunk);
+}
+void ora_add(int V, int N, double* dst, const double* src, const double* M) { add(V, N, C(dst), C(src), C(M)); }
+void ora_add_scalar(int V, int N, double* dst, const double* src, double s) { add_scalar(V, N, C(dst), C(src), s); }
+void ora_rescale_add(int V, int N, double* dst, const double* L, const double* src, double r) {
+  rescale_add(V, N, C(dst), C(L), C(src), r);
+}
+void ora_trsm_upper_rhs(int V, int N, double* q, const double* R) { trsm_upper_rhs(V, N, C(q), C(R)); }
+void ora_thinQR(int V, int N, double* q, double* R, int chunk) { thinQR(V, N, C(q), C(R), chunk); }
+int ora_llt_upper(int N, const double* A, double* R) { return llt_upper(N, C(A), C(R)); }
+void ora_fullpivlu_inverse(int N, const double* A, double* X) { fullpivlu_inverse(N, C(A), C(X)); }
+void ora_fullpivlu_solve(int N, const double* A, const double* B, double* X) {
+  fullpivlu_solve(N, C(A), C(B), N, C(X));
+}
+
+// inc/block_solvers.hpp:10-45
+int ora_BCG(int V, int N, double mass, const double* U_, const double* B_, double* X_, double eps, int max_it,
+            int chunk, double* seconds) {
+  const cd *U = C(U_), *B = C(B_);
+  cd* X = C(X_);
+  const size_t n = static_cast<size_t>(V) * N * 3, nn = static_cast<size_t>(N) * N;
+  double t0 = now();
+  std::fill(X, X + n, cd(0));
+  cvec T(n, cd(0)), P(B, B + n), R(B, B + n);
+  cvec r2(nn), r2_old(nn), alpha(nn), beta(nn), pt(nn), nalpha(nn);
+  hermitian_dot(V, N, R.data(), R.data(), r2.data(), chunk);
+  std::vector<double> rn(N);
+  for (int i = 0; i < N; ++i) rn[i] = std::sqrt(r2[midx(N, i, i)].real());
+  double residual = 1.0;
+  int iter = 0;
+  while (residual > eps && iter < max_it) {
+    op(V, N, mass, U, P.data(), T.data(), 0.0);
+    ++iter;
+    hermitian_dot(V, N, P.data(), T.data(), pt.data(), chunk);
+    fullpivlu_solve(N, pt.data(), r2.data(), N, alpha.data());
+    for (size_t k = 0; k < nn; ++k) nalpha[k] = -alpha[k];
+    add(V, N, R.data(), T.data(), nalpha.data());
+    r2_old = r2;
+    hermitian_dot(V, N, R.data(), R.data(), r2.data(), chunk);
+    fullpivlu_solve(N, r2_old.data(), r2.data(), N, beta.data());
+    add(V, N, X, P.data(), alpha.data());
+    rescale_add(V, N, P.data(), beta.data(), R.data(), 1.0);
+    residual = 0;
+    for (int i = 0; i < N; ++i) residual = std::max(residual, std::sqrt(r2[midx(N, i, i)].real()) / rn[i]);
+  }
+  if (seconds) *seconds = now() - t0;
+  return iter;
+}
+
+// inc/block_solvers.hpp:50-86
+int ora_BCGrQ(int V, int N, double mass, const double* U_, const double* B_, double* X_, double eps, int max_it,
+              int chunk, double* seconds) {
+  const cd *U = C(U_), *B = C(B_);
+  cd* X = C(X_);
+  const size_t n = static_cast<size_t>(V) * N * 3, nn = static_cast<size_t>(N) * N;
+  double t0 = now();
+  std::fill(X, X + n, cd(0));
+  cvec T(n, cd(0)), Q(B, B + n);
+  cvec alpha(nn), rho(nn), delta(nn), pt(nn), nalpha(nn), ad(nn), rhoH(nn);
+  thinQR(V, N, Q.data(), delta.data(), chunk);
+  cvec P(Q);
+  std::vector<double> rn(N), dn(N);
+  rownorms(N, delta.data(), rn.data());
+  int iter = 0;
+  double residual = 1.0;
+  while (residual > eps && iter < max_it) {
+    op(V, N, mass, U, P.data(), T.data(), 0.0);
+    ++iter;
+    hermitian_dot(V, N, P.data(), T.data(), pt.data(), chunk);
+    fullpivlu_inverse(N, pt.data(), alpha.data());
+    for (size_t k = 0; k < nn; ++k) nalpha[k] = -alpha[k];
+    add(V, N, Q.data(), T.data(), nalpha.data());
+    thinQR(V, N, Q.data(), rho.data(), chunk);
+    mm(N, alpha.data(), delta.data(), ad.data());
+    add(V, N, X, P.data(), ad.data());
+    adjoint(N, rho.data(), rhoH.data());
+    rescale_add(V, N, P.data(), rhoH.data(), Q.data(), 1.0);
+    mm(N, rho.data(), delta.data(), delta.data());
+    rownorms(N, delta.data(), dn.data());
+    residual = 0;
+    for (int i = 0; i < N; ++i) residual = std::max(residual, dn[i] / rn[i]);
+  }
+  if (seconds) *seconds = now() - t0;
+  return iter;
+}
+
+// inc/block_solvers.hpp:91-185 (state machine: SURVEY Appendix A).
+// X_: [S][V][N][3].  n_unconverged_out (optional) receives the final count.
+int ora_SBCGrQ(int V, int N, double mass, const double* U_, const double* B_, double* X_, const double* sigma,
+               int S, double eps, double eps_shifts, int max_it, int chunk, double* seconds,
+               int* n_unconverged_out) {
+  const cd *U = C(U_), *B = C(B_);
+  const size_t n = static_cast<size_t>(V) * N * 3, nn = static_cast<size_t>(N) * N;
+  double t0 = now();
+  int n_unconv = S;
+  cvec I(nn), alpha(nn), rho(nn), delta(nn), alpha_inv(nn), alpha_inv_old(nn), rho_old(nn);
+  identity(N, I.data());
+  alpha_inv = I;
+  cvec T(B, B + n), Q(B, B + n);
+  std::vector<cd*> X(S);
+  for (int s = 0; s < S; ++s) {
+    X[s] = C(X_) + static_cast<size_t>(s) * n;
+    std::fill(X[s], X[s] + n, cd(0));
+  }
+  thinQR(V, N, Q.data(), delta.data(), chunk);
+  rho = delta;
+  std::vector<cvec> P(S, Q);
+  cvec beta_s_inv(nn), t1(nn), t2(nn), ad(nn), nalpha(nn), rhoH(nn), rho_oldH(nn);
+  std::vector<cvec> alpha_s(S, I), beta_s(S, I);
+  int iter = 0;
+  std::vector<double> b_norm(N), dn(N);
+  rownorms(N, delta.data(), b_norm.data());
+  double residual = 1.0;
+  while (residual > eps && iter < max_it) {
+    op(V, N, mass, U, P[0].data(), T.data(), 0.0);   // :134
+    add_scalar(V, N, T.data(), P[0].data(), sigma[0]);  // :136
+    ++iter;
+    alpha_inv_old = alpha_inv;
+    hermitian_dot(V, N, P[0].data(), T.data(), alpha_inv.data(), chunk);  // :140
+    fullpivlu_inverse(N, alpha_inv.data(), alpha.data());                 // :142
+    mm(N, alpha.data(), delta.data(), ad.data());
+    add(V, N, X[0], P[0].data(), ad.data());  // :145 (old delta)
+    for (size_t k = 0; k < nn; ++k) nalpha[k] = -alpha[k];
+    add(V, N, Q.data(), T.data(), nalpha.data());  // :148
+    rho_old = rho;
+    thinQR(V, N, Q.data(), rho.data(), chunk);  // :152
+    mm(N, rho.data(), delta.data(), delta.data());
+    rownorms(N, delta.data(), dn.data());
+    residual = 0;
+    for (int i = 0; i < N; ++i) residual = std::max(residual, dn[i] / b_norm[i]);
+    adjoint(N, rho.data(), rhoH.data());
+    rescale_add(V, N, P[0].data(), rhoH.data(), Q.data(), 1.0);  // :158
+    adjoint(N, rho_old.data(), rho_oldH.data());
+    const int n_loop = n_unconv;
+    for (int s = n_loop - 1; s > 0; --s) {
+      // beta_s_inv = I + (sigma_s - sigma_0) alpha + alpha rho_old alpha_inv_old (I - beta_s) rho_old^dag  (:163-165)
+      mm(N, alpha.data(), rho_old.data(), t1.data());
+      mm(N, t1.data(), alpha_inv_old.data(), t1.data());
+      for (size_t k = 0; k < nn; ++k) t2[k] = I[k] - beta_s[s][k];
+      mm(N, t1.data(), t2.data(), t1.data());
+      mm(N, t1.data(), rho_oldH.data(), t1.data());
+      const double ds = sigma[s] - sigma[0];
+      for (size_t k = 0; k < nn; ++k) beta_s_inv[k] = (I[k] + ds * alpha[k]) + t1[k];
+      fullpivlu_inverse(N, beta_s_inv.data(), beta_s[s].data());  // :166
+      // alpha_s = beta_s alpha rho_old alpha_inv_old alpha_s  (:167-168), left to right
+      mm(N, beta_s[s].data(), alpha.data(), t1.data());
+      mm(N, t1.data(), rho_old.data(), t1.data());
+      mm(N, t1.data(), alpha_inv_old.data(), t1.data());
+      mm(N, t1.data(), alpha_s[s].data(), alpha_s[s].data());
+      // residual_shift = max_i rownorm_i(rho alpha_inv alpha_s) / b_norm_i  (:169-172)
+      mm(N, rho.data(), alpha_inv.data(), t1.data());
+      mm(N, t1.data(), alpha_s[s].data(), t1.data());
+      rownorms(N, t1.data(), dn.data());
+      double rs = 0;
+      for (int i = 0; i < N; ++i) rs = std::max(rs, dn[i] / b_norm[i]);
+      add(V, N, X[s], P[s].data(), alpha_s[s].data());  // :175
+      mm(N, beta_s[s].data(), rhoH.data(), t1.data());
+      rescale_add(V, N, P[s].data(), t1.data(), Q.data(), 1.0);  // :177
+      if (rs < eps_shifts) --n_unconv;                           // :179-181
+    }
+  }
+  if (seconds) *seconds = now() - t0;
+  if (n_unconverged_out) *n_unconverged_out = n_unconv;
+  return iter;
+}
+
+// true relative residual per rhs, as benchmark.cpp:93-103 / test/solvers.cpp:99-118:
+// sqrt( diag((A+sigma)X - B)^dag(...) / diag(B^dag B) ), out[N]
+void ora_true_residual(int V, int N, double mass, const double* U_, const double* B_, const double* X_,
+                       double sigma, double* out) {
+  const size_t n = static_cast<size_t>(V) * N * 3, nn = static_cast<size_t>(N) * N;
+  cvec AX(n), b2(nn), r2(nn);
+  op(V, N, mass, C(U_), C(X_), AX.data(), 0.0);
+  add_scalar(V, N, AX.data(), C(X_), sigma);
+  for (size_t k = 0; k < n; ++k) AX[k] -= C(B_)[k];
+  hermitian_dot(V, N, C(B_), C(B_), b2.data(), 0);
+  hermitian_dot(V, N, AX.data(), AX.data(), r2.data(), 0);
+  for (int i = 0; i < N; ++i) out[i] = std::sqrt(r2[midx(N, i, i)].real() / b2[midx(N, i, i)].real());
+}
+
+}  // extern "C"
