@@ -1,0 +1,934 @@
+// C-ABI of the block-CG hot path (include/blockcg_b200.h): context, fields,
+// primitives and the device-resident BCG / BCGrQ / SBCGrQ loops.
+//
+// Loop control: all coefficients and the convergence test live on the device
+// (small_kernels.cuh).  The host enqueues CUDA graphs holding a batch of
+// iterations each, without waiting; after every batch the control block is
+// copied to a pinned mirror and the host looks at the *previous* batch's
+// mirror, so the GPU never idles waiting for the host and the host never
+// synchronises per iteration.  Once `done` is set the remaining kernels of
+// in-flight batches return immediately.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/blockcg_b200.h"
+#include "nlist.h"
+#include "ops.cuh"
+#include "small_kernels.cuh"
+
+namespace bcg {
+#define BCG_DECL(n) const OpsTable* get_ops_##n();
+BCG_FOR_EACH_N(BCG_DECL)
+#undef BCG_DECL
+const OpsTable* get_ops(int N) {
+  switch (N) {
+#define BCG_CASE(n) \
+  case n:           \
+    return get_ops_##n();
+    BCG_FOR_EACH_N(BCG_CASE)
+#undef BCG_CASE
+    default:
+      return nullptr;
+  }
+}
+}  // namespace bcg
+
+using namespace bcg;
+
+struct GraphCache {
+  cudaGraphExec_t exec = nullptr;
+  int kind = -1;  // 0 BCG, 1 (S)BCGrQ
+  int n_shifts = 0;
+  int batch = 0;
+  int launches = 0;
+  std::vector<const void*> key;
+};
+
+struct bcg_ctx {
+  int device = 0, rank = 0, nranks = 1;
+  long long V = 0;
+  int N = 0, S = 1, sms = 0;
+  double mass = 0.0;
+  bool links_set = false;
+  cudaStream_t stream = nullptr;
+  const OpsTable* ops = nullptr;
+  cd* U_alloc = nullptr;
+  std::vector<cd*> fields;  // allocation base (halo included); site 0 at +2*3N
+  cd* gpart = nullptr;
+  size_t gpart_elems = 0;
+  cd* gred = nullptr;  // reduced Gram (multi-rank path / primitives): N*N
+  cd* mats = nullptr;
+  MatLayout L{};
+  double* b_norm = nullptr;
+  Ctrl* ctrl = nullptr;
+  Ctrl* ctrl_host = nullptr;  // pinned, 2 slots
+  cd* mat_host = nullptr;     // pinned staging for N*N matrices (4 slots)
+  int work_T = -1, work_Q = -1;
+  std::vector<int> work_P;
+  std::vector<int> host_X;  // handles used by the host-buffer entry points
+  int host_B = -1;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_batch[2] = {nullptr, nullptr};
+  ncclComm_t comm = nullptr;
+  bool comm_ready = false;
+  GraphCache graph;
+  std::string err;
+  size_t small_smem = 0;
+};
+
+namespace {
+
+int fail(bcg_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(c, BCG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                       \
+  } while (0)
+#define NC(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t e_ = (call);                                                                      \
+    if (e_ != ncclSuccess)                                                                         \
+      return fail(c, BCG_ERR_NCCL, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                       \
+  } while (0)
+#define KL(expr)                                                                                 \
+  do {                                                                                           \
+    int r_ = (expr);                                                                             \
+    if (r_ < 0)                                                                                  \
+      return fail(c, BCG_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                           \
+                  cudaGetErrorString(static_cast<cudaError_t>(-r_)), __FILE__, __LINE__);        \
+  } while (0)
+
+inline size_t site_elems(const bcg_ctx* c) { return static_cast<size_t>(3) * c->N; }
+inline size_t field_elems(const bcg_ctx* c) { return static_cast<size_t>(c->V + 4) * site_elems(c); }
+inline cd* fptr(const bcg_ctx* c, int h) { return c->fields[h] + 2 * site_elems(c); }
+inline cd* uptr(const bcg_ctx* c) { return c->U_alloc + 2 * 9; }
+inline bool valid(const bcg_ctx* c, int h) {
+  return h >= 0 && h < static_cast<int>(c->fields.size()) && c->fields[h] != nullptr;
+}
+inline cd* mat(const bcg_ctx* c, int slot) { return c->mats + c->L.fixed(slot); }
+
+int field_alloc(bcg_ctx* c, int* h) {
+  cd* p = nullptr;
+  CU(cudaMalloc(&p, field_elems(c) * sizeof(cd)));
+  CU(cudaMemsetAsync(p, 0, field_elems(c) * sizeof(cd), c->stream));
+  for (size_t i = 0; i < c->fields.size(); ++i)
+    if (c->fields[i] == nullptr) {
+      c->fields[i] = p;
+      *h = static_cast<int>(i);
+      return BCG_OK;
+    }
+  c->fields.push_back(p);
+  *h = static_cast<int>(c->fields.size()) - 1;
+  return BCG_OK;
+}
+
+// Fill the 2+2 halo sites of a field (site = 3N) or of the links (site = 9).
+int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
+  if (c->nranks == 1) {
+    const int n = 4 * site;
+    halo_wrap_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(f, c->V, site, ctrl);
+    if (launches) ++*launches;
+    CU(cudaGetLastError());
+    return BCG_OK;
+  }
+  if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
+  if (c->V < 2) return fail(c, BCG_ERR_INVALID, "slab decomposition needs >= 2 sites per rank");
+  const int left = (c->rank + c->nranks - 1) % c->nranks, right = (c->rank + 1) % c->nranks;
+  const size_t cnt = static_cast<size_t>(2) * site * 2;  // doubles
+  // boundary sites are contiguous in the field and halo slots are contiguous too:
+  // no pack/unpack kernels, NCCL moves them directly over NVLink.
+  NC(ncclGroupStart());
+  NC(ncclSend(f, cnt, ncclDouble, left, c->comm, c->stream));                                   // sites 0,1
+  NC(ncclSend(f + (c->V - 2) * site, cnt, ncclDouble, right, c->comm, c->stream));              // sites V-2,V-1
+  NC(ncclRecv(f + c->V * site, cnt, ncclDouble, right, c->comm, c->stream));                    // slots V,V+1
+  NC(ncclRecv(f - 2 * static_cast<long long>(site), cnt, ncclDouble, left, c->comm, c->stream));  // slots -2,-1
+  NC(ncclGroupEnd());
+  return BCG_OK;
+}
+
+// Partial Grams -> what the coefficient kernels consume.  Single rank: the
+// partials themselves (reduced in fixed order inside the coefficient kernel).
+// Multi rank: reduce locally, all-reduce the N x N block over NVLink, hand the
+// kernels one "partial".
+int gram_finalize(bcg_ctx* c, int nparts, const cd** src, int* nsrc, int* launches) {
+  if (c->nranks == 1) {
+    *src = c->gpart;
+    *nsrc = nparts;
+    return BCG_OK;
+  }
+  if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
+  const size_t nn = c->L.nn();
+  gram_reduce_kernel<<<1, kSmallThreads, nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, nparts, c->N);
+  if (launches) ++*launches;
+  CU(cudaGetLastError());
+  NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
+  *src = c->gred;
+  *nsrc = 1;
+  return BCG_OK;
+}
+
+// reduced Gram a^dag b into device buffer c->gred
+int gram_to_gred(bcg_ctx* c, const cd* a, const cd* b, int* launches) {
+  int np = c->ops->gram(c->stream, a, b, c->V, c->gpart, nullptr, c->sms, launches);
+  KL(np);
+  const size_t nn = c->L.nn();
+  gram_reduce_kernel<<<1, kSmallThreads, nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
+  if (launches) ++*launches;
+  CU(cudaGetLastError());
+  if (c->nranks > 1) {
+    if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
+    NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
+  }
+  return BCG_OK;
+}
+
+int upload_mat(bcg_ctx* c, int slot, const double* host, int staging) {
+  const size_t nn = c->L.nn();
+  std::memcpy(c->mat_host + staging * nn, host, nn * sizeof(cd));
+  CU(cudaMemcpyAsync(mat(c, slot), c->mat_host + staging * nn, nn * sizeof(cd), cudaMemcpyHostToDevice, c->stream));
+  return BCG_OK;
+}
+
+int ensure_work(bcg_ctx* c, int n_shifts) {
+  if (c->work_T < 0) {
+    int r = field_alloc(c, &c->work_T);
+    if (r) return r;
+  }
+  if (c->work_Q < 0) {
+    int r = field_alloc(c, &c->work_Q);
+    if (r) return r;
+  }
+  while (static_cast<int>(c->work_P.size()) < n_shifts) {
+    int h;
+    int r = field_alloc(c, &h);
+    if (r) return r;
+    c->work_P.push_back(h);
+  }
+  return BCG_OK;
+}
+
+int pick_batch(const bcg_ctx* c, int n_shifts) {
+  // aim at ~2 ms of device work per graph launch
+  const double F = 48.0 * c->N * static_cast<double>(c->V);
+  double us = (7.0 + 4.0 * n_shifts) * F / 6.0e6 + 25.0;
+  int b = static_cast<int>(2000.0 / us);
+  if (b < 2) b = 2;
+  if (b > 48) b = 48;
+  return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bcg_version(void) { return "blockcg_b200 0.1 (sm_100a)"; }
+int bcg_supports_nrhs(int n) { return get_ops(n) != nullptr; }
+const char* bcg_last_error(const bcg_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, int device, int rank, int nranks) {
+  if (!out) return BCG_ERR_INVALID;
+  *out = nullptr;
+  bcg_ctx* c = new bcg_ctx();
+  *out = c;  // returned even on failure so the message can be read; destroy() is safe
+  if (v_local < 1 || max_shifts < 1 || max_shifts > BCG_MAX_SHIFTS || nranks < 1 || rank < 0 || rank >= nranks)
+    return fail(c, BCG_ERR_INVALID, "bad argument (v_local=%lld max_shifts=%d rank=%d/%d)", (long long)v_local,
+                max_shifts, rank, nranks);
+  c->ops = get_ops(n_rhs);
+  if (!c->ops) return fail(c, BCG_ERR_INVALID, "N_rhs=%d is not compiled in", n_rhs);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(c, BCG_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  c->device = device;
+  c->rank = rank;
+  c->nranks = nranks;
+  c->V = v_local;
+  c->N = n_rhs;
+  c->S = max_shifts;
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(c, BCG_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  c->sms = prop.multiProcessorCount;
+  c->ops->prepare(c->sms);
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->L.N = n_rhs;
+  c->L.S = max_shifts;
+  c->gpart_elems = static_cast<size_t>(c->ops->max_partials(c->sms)) * c->L.nn();
+  CU(cudaMalloc(&c->gpart, c->gpart_elems * sizeof(cd)));
+  CU(cudaMalloc(&c->gred, c->L.nn() * sizeof(cd)));
+  CU(cudaMalloc(&c->mats, c->L.total() * sizeof(cd)));
+  CU(cudaMemset(c->mats, 0, c->L.total() * sizeof(cd)));
+  CU(cudaMalloc(&c->b_norm, sizeof(double) * n_rhs));
+  CU(cudaMalloc(&c->ctrl, sizeof(Ctrl)));
+  CU(cudaMemset(c->ctrl, 0, sizeof(Ctrl)));
+  CU(cudaMallocHost(&c->ctrl_host, 2 * sizeof(Ctrl)));
+  CU(cudaMallocHost(&c->mat_host, 4 * c->L.nn() * sizeof(cd)));
+  CU(cudaMalloc(&c->U_alloc, static_cast<size_t>(c->V + 4) * 9 * sizeof(cd)));
+  for (auto& e : c->ev) CU(cudaEventCreate(&e));
+  for (auto& e : c->ev_batch) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  c->small_smem = SmallSmem::bytes(n_rhs);
+  if (c->small_smem > 48 * 1024) {
+    const int b = static_cast<int>(c->small_smem);
+    CU(cudaFuncSetAttribute(rq_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CU(cudaFuncSetAttribute(rq_step_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CU(cudaFuncSetAttribute(rq_step_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CU(cudaFuncSetAttribute(bcg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CU(cudaFuncSetAttribute(bcg_step_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CU(cudaFuncSetAttribute(bcg_step_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CU(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+  }
+  return BCG_OK;
+}
+
+int bcg_ctx_destroy(bcg_ctx* c) {
+  if (!c) return BCG_OK;
+  if (c->stream) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+  }
+  if (c->graph.exec) cudaGraphExecDestroy(c->graph.exec);
+  if (c->comm) ncclCommDestroy(c->comm);
+  for (cd* p : c->fields)
+    if (p) cudaFree(p);
+  cudaFree(c->U_alloc);
+  cudaFree(c->gpart);
+  cudaFree(c->gred);
+  cudaFree(c->mats);
+  cudaFree(c->b_norm);
+  cudaFree(c->ctrl);
+  if (c->ctrl_host) cudaFreeHost(c->ctrl_host);
+  if (c->mat_host) cudaFreeHost(c->mat_host);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_batch)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return BCG_OK;
+}
+
+int bcg_comm_get_unique_id(void* id_out) {
+  static_assert(sizeof(ncclUniqueId) <= BCG_UNIQUE_ID_BYTES, "id size");
+  if (!id_out) return BCG_ERR_INVALID;
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return BCG_ERR_NCCL;
+  std::memset(id_out, 0, BCG_UNIQUE_ID_BYTES);
+  std::memcpy(id_out, &id, sizeof id);
+  return BCG_OK;
+}
+
+int bcg_comm_init(bcg_ctx* c, const void* id_in) {
+  if (!c || !id_in) return BCG_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id_in, sizeof id);
+  NC(ncclCommInitRank(&c->comm, c->nranks, id, c->rank));
+  c->comm_ready = true;
+  return BCG_OK;
+}
+
+int bcg_set_links(bcg_ctx* c, const double* links_host, double mass) {
+  if (!c || !links_host) return fail(c, BCG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(uptr(c), links_host, static_cast<size_t>(c->V) * 9 * sizeof(cd), cudaMemcpyHostToDevice,
+                     c->stream));
+  int r = halo_refresh(c, uptr(c), 9, nullptr, nullptr);
+  if (r) return r;
+  CU(cudaStreamSynchronize(c->stream));
+  c->mass = mass;
+  c->links_set = true;
+  return BCG_OK;
+}
+
+int bcg_field_alloc(bcg_ctx* c, int* h) {
+  if (!c || !h) return fail(c, BCG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  return field_alloc(c, h);
+}
+int bcg_field_free(bcg_ctx* c, int h) {
+  if (!c || !valid(c, h)) return fail(c, BCG_ERR_INVALID, "bad field handle %d", h);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaFree(c->fields[h]));
+  c->fields[h] = nullptr;
+  return BCG_OK;
+}
+int bcg_field_upload(bcg_ctx* c, int h, const double* host) {
+  if (!c || !valid(c, h) || !host) return fail(c, BCG_ERR_INVALID, "bad argument to field_upload");
+  CU(cudaMemcpyAsync(fptr(c, h), host, static_cast<size_t>(c->V) * site_elems(c) * sizeof(cd),
+                     cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+int bcg_field_download(bcg_ctx* c, int h, double* host) {
+  if (!c || !valid(c, h) || !host) return fail(c, BCG_ERR_INVALID, "bad argument to field_download");
+  CU(cudaMemcpyAsync(host, fptr(c, h), static_cast<size_t>(c->V) * site_elems(c) * sizeof(cd),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+int bcg_field_zero(bcg_ctx* c, int h) {
+  if (!c || !valid(c, h)) return fail(c, BCG_ERR_INVALID, "bad field handle %d", h);
+  CU(cudaMemsetAsync(c->fields[h], 0, field_elems(c) * sizeof(cd), c->stream));
+  return BCG_OK;
+}
+int bcg_field_copy(bcg_ctx* c, int dst, int src) {
+  if (!c || !valid(c, dst) || !valid(c, src)) return fail(c, BCG_ERR_INVALID, "bad field handle");
+  CU(cudaMemcpyAsync(c->fields[dst], c->fields[src], field_elems(c) * sizeof(cd), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  return BCG_OK;
+}
+
+// ---- primitives ---------------------------------------------------------------------------
+int bcg_op(bcg_ctx* c, int out, int in, double sigma, double* gram_host) {
+  if (!c || !valid(c, out) || !valid(c, in) || out == in) return fail(c, BCG_ERR_INVALID, "bad field handle");
+  if (!c->links_set) return fail(c, BCG_ERR_INVALID, "bcg_set_links has not been called");
+  CU(cudaSetDevice(c->device));
+  int r = halo_refresh(c, fptr(c, in), 3 * c->N, nullptr, nullptr);
+  if (r) return r;
+  int np = c->ops->dirac(c->stream, fptr(c, in), fptr(c, out), uptr(c), c->V, c->mass * c->mass, sigma,
+                         gram_host ? c->gpart : nullptr, nullptr, c->sms, nullptr);
+  KL(np);
+  if (gram_host) {
+    const size_t nn = c->L.nn();
+    gram_reduce_kernel<<<1, kSmallThreads, nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
+    CU(cudaGetLastError());
+    if (c->nranks > 1) NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
+    CU(cudaMemcpyAsync(gram_host, c->gred, nn * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+
+int bcg_gram(bcg_ctx* c, int a, int b, double* r_host) {
+  if (!c || !valid(c, a) || !valid(c, b) || !r_host) return fail(c, BCG_ERR_INVALID, "bad argument to gram");
+  CU(cudaSetDevice(c->device));
+  int r = gram_to_gred(c, fptr(c, a), fptr(c, b), nullptr);
+  if (r) return r;
+  CU(cudaMemcpyAsync(r_host, c->gred, c->L.nn() * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+
+int bcg_add(bcg_ctx* c, int dst, int src, const double* m_host) {
+  if (!c || !valid(c, dst) || !valid(c, src) || !m_host || dst == src)
+    return fail(c, BCG_ERR_INVALID, "bad argument to add");
+  CU(cudaSetDevice(c->device));
+  int r = upload_mat(c, M_SCRATCH, m_host, 0);
+  if (r) return r;
+  KL(c->ops->axpy_gram(c->stream, fptr(c, dst), fptr(c, src), mat(c, M_SCRATCH), c->V, nullptr, nullptr, c->sms,
+                       nullptr));
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+
+int bcg_add_scalar(bcg_ctx* c, int dst, int src, double s) {
+  if (!c || !valid(c, dst) || !valid(c, src)) return fail(c, BCG_ERR_INVALID, "bad argument to add_scalar");
+  CU(cudaSetDevice(c->device));
+  const long long n = c->V * static_cast<long long>(site_elems(c));
+  axpy_scalar_kernel<<<c->sms * 8, 256, 0, c->stream>>>(fptr(c, dst), fptr(c, src), s, n);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+
+int bcg_rescale_add(bcg_ctx* c, int dst, const double* l_host, int src, double r) {
+  if (!c || !valid(c, dst) || !valid(c, src) || !l_host || dst == src)
+    return fail(c, BCG_ERR_INVALID, "bad argument to rescale_add");
+  CU(cudaSetDevice(c->device));
+  int rr = upload_mat(c, M_SCRATCH, l_host, 0);
+  if (rr) return rr;
+  KL(c->ops->rescale_add(c->stream, fptr(c, dst), mat(c, M_SCRATCH), fptr(c, src), r, c->V, c->sms, nullptr));
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+
+int bcg_trsm(bcg_ctx* c, int q, const double* r_host) {
+  if (!c || !valid(c, q) || !r_host) return fail(c, BCG_ERR_INVALID, "bad argument to trsm");
+  CU(cudaSetDevice(c->device));
+  int rr = upload_mat(c, M_SCRATCH, r_host, 0);
+  if (rr) return rr;
+  KL(c->ops->trsm(c->stream, fptr(c, q), mat(c, M_SCRATCH), c->V, nullptr, c->sms, nullptr));
+  CU(cudaStreamSynchronize(c->stream));
+  return BCG_OK;
+}
+
+int bcg_thinqr(bcg_ctx* c, int q, double* r_host) {
+  if (!c || !valid(c, q) || !r_host) return fail(c, BCG_ERR_INVALID, "bad argument to thinqr");
+  CU(cudaSetDevice(c->device));
+  int r = gram_to_gred(c, fptr(c, q), fptr(c, q), nullptr);
+  if (r) return r;
+  CU(cudaMemsetAsync(c->ctrl, 0, sizeof(Ctrl), c->stream));
+  chol_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(mat(c, M_SCRATCH), c->gred, c->N, c->ctrl);
+  CU(cudaGetLastError());
+  KL(c->ops->trsm(c->stream, fptr(c, q), mat(c, M_SCRATCH), c->V, nullptr, c->sms, nullptr));
+  CU(cudaMemcpyAsync(r_host, mat(c, M_SCRATCH), c->L.nn() * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->ctrl_host, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->ctrl_host->status == BCG_ERR_NOT_PD) return fail(c, BCG_ERR_NOT_PD, "thinQR: Gram matrix not positive definite");
+  return BCG_OK;
+}
+
+int bcg_true_residual(bcg_ctx* c, int x, int b, double sigma, double* res_host) {
+  if (!c || !valid(c, x) || !valid(c, b) || !res_host) return fail(c, BCG_ERR_INVALID, "bad argument to true_residual");
+  if (!c->links_set) return fail(c, BCG_ERR_INVALID, "bcg_set_links has not been called");
+  CU(cudaSetDevice(c->device));
+  int r = ensure_work(c, 0);
+  if (r) return r;
+  r = halo_refresh(c, fptr(c, x), 3 * c->N, nullptr, nullptr);
+  if (r) return r;
+  cd* T = fptr(c, c->work_T);
+  KL(c->ops->dirac(c->stream, fptr(c, x), T, uptr(c), c->V, c->mass * c->mass, sigma, nullptr, nullptr, c->sms,
+                   nullptr));
+  const long long n = c->V * static_cast<long long>(site_elems(c));
+  sub_kernel<<<c->sms * 8, 256, 0, c->stream>>>(T, T, fptr(c, b), n);
+  CU(cudaGetLastError());
+  const size_t nn = c->L.nn();
+  std::vector<cd> r2(nn), b2(nn);
+  r = gram_to_gred(c, T, T, nullptr);
+  if (r) return r;
+  CU(cudaMemcpyAsync(c->mat_host, c->gred, nn * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::memcpy(r2.data(), c->mat_host, nn * sizeof(cd));
+  r = gram_to_gred(c, fptr(c, b), fptr(c, b), nullptr);
+  if (r) return r;
+  CU(cudaMemcpyAsync(c->mat_host, c->gred, nn * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::memcpy(b2.data(), c->mat_host, nn * sizeof(cd));
+  for (int i = 0; i < c->N; ++i) res_host[i] = std::sqrt(r2[i + c->N * i].x / b2[i + c->N * i].x);
+  return BCG_OK;
+}
+
+}  // extern "C"
+
+// ---- the iteration loops ---------------------------------------------------------------------
+namespace {
+
+struct LoopPlan {
+  int kind;  // 0 BCG, 1 (S)BCGrQ
+  int n_shifts;
+  cd* P0;
+  cd* T;
+  cd* Q;  // BCG: R
+  ShiftPtrs fp;
+  double sigma0;
+};
+
+// enqueue one iteration on c->stream
+int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
+  const cd* gsrc;
+  int nsrc;
+  int np = c->ops->dirac(c->stream, p.P0, p.T, uptr(c), c->V, c->mass * c->mass, p.sigma0, c->gpart, c->ctrl,
+                         c->sms, launches);
+  KL(np);
+  int r = gram_finalize(c, np, &gsrc, &nsrc, launches);
+  if (r) return r;
+  if (p.kind == 1)
+    rq_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl);
+  else
+    bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl);
+  ++*launches;
+  CU(cudaGetLastError());
+  np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches);
+  KL(np);
+  r = gram_finalize(c, np, &gsrc, &nsrc, launches);
+  if (r) return r;
+  if (p.kind == 1)
+    rq_step_b_kernel<<<p.n_shifts, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc,
+                                                                             c->ctrl);
+  else
+    bcg_step_b_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc, c->ctrl);
+  ++*launches;
+  CU(cudaGetLastError());
+  KL(c->ops->shift_update(c->stream, p.Q, &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
+                          p.kind == 1 ? 1 : 0, p.kind == 1 ? 0 : 1, c->ctrl, c->sms, launches));
+  return halo_refresh(c, p.P0, 3 * c->N, c->ctrl, launches);
+}
+
+int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launches_total) {
+  const int batch = pick_batch(c, p.n_shifts);
+  // (re)build the graph of `batch` iterations if anything it bakes in changed
+  std::vector<const void*> key = {p.P0, p.T, p.Q};
+  for (int s = 0; s < p.n_shifts; ++s) {
+    key.push_back(p.fp.X[s]);
+    key.push_back(p.fp.P[s]);
+  }
+  double sig = p.sigma0;
+  const void* sigbits;
+  std::memcpy(&sigbits, &sig, sizeof sigbits);
+  key.push_back(sigbits);
+  GraphCache& g = c->graph;
+  if (!g.exec || g.kind != p.kind || g.n_shifts != p.n_shifts || g.batch != batch || g.key != key) {
+    if (g.exec) {
+      cudaGraphExecDestroy(g.exec);
+      g.exec = nullptr;
+    }
+    int launches = 0;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int r = BCG_OK;
+    for (int i = 0; i < batch && r == BCG_OK; ++i) r = enqueue_iteration(c, p, &launches);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (r != BCG_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return r;
+    }
+    if (e != cudaSuccess) return fail(c, BCG_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(c, BCG_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    g.kind = p.kind;
+    g.n_shifts = p.n_shifts;
+    g.batch = batch;
+    g.launches = launches;
+    g.key = key;
+  }
+  // pipelined submission: look at batch i-1's mirror after submitting batch i
+  int submitted = 0;
+  bool done = false;
+  while (!done) {
+    CU(cudaGraphLaunch(g.exec, c->stream));
+    *launches_total += g.launches;
+    const int slot = submitted & 1;
+    CU(cudaMemcpyAsync(c->ctrl_host + slot, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev_batch[slot], c->stream));
+    ++submitted;
+    if (submitted >= 2) {
+      const int prev = (submitted - 2) & 1;
+      CU(cudaEventSynchronize(c->ev_batch[prev]));
+      done = c->ctrl_host[prev].done != 0;
+    }
+  }
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const Ctrl& fin = c->ctrl_host[(submitted - 1) & 1];
+  if (info) {
+    info->iterations = fin.iter;
+    info->residual = fin.residual;
+    info->n_unconverged = fin.n_unconv;
+  }
+  if (fin.status == BCG_ERR_NOT_PD)
+    return fail(c, BCG_ERR_NOT_PD, "Gram matrix not positive definite at iteration %d", fin.iter);
+  return BCG_OK;
+}
+
+int init_ctrl(bcg_ctx* c, int n_shifts, const double* sigma, double eps, double eps_shifts, int max_it) {
+  Ctrl h;
+  std::memset(&h, 0, sizeof h);
+  h.n_unconv = n_shifts;
+  h.n_shifts = n_shifts;
+  h.max_it = max_it;
+  h.eps = eps;
+  h.eps_shifts = eps_shifts;
+  h.residual = 1.0;
+  for (int s = 0; s < n_shifts; ++s) h.sigma[s] = sigma ? sigma[s] : 0.0;
+  c->ctrl_host[0] = h;
+  CU(cudaMemcpyAsync(c->ctrl, c->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // ctrl_host[0] is reused as a mirror by the loop
+  return BCG_OK;
+}
+
+int finish_info(bcg_ctx* c, bcg_solve_info* info, int64_t launches) {
+  if (!info) return BCG_OK;
+  float ms_setup = 0, ms_loop = 0;
+  CU(cudaEventElapsedTime(&ms_setup, c->ev[0], c->ev[1]));
+  CU(cudaEventElapsedTime(&ms_loop, c->ev[1], c->ev[2]));
+  info->setup_ms = ms_setup;
+  info->solve_ms = ms_loop;
+  info->kernel_launches = launches;
+  return BCG_OK;
+}
+
+int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts, double eps, double eps_shifts,
+             int max_it, bcg_solve_info* info) {
+  if (!c) return BCG_ERR_INVALID;
+  if (!xh || !valid(c, b) || n_shifts < 1 || n_shifts > c->S)
+    return fail(c, BCG_ERR_INVALID, "bad argument (n_shifts=%d, context max %d)", n_shifts, c->S);
+  for (int s = 0; s < n_shifts; ++s)
+    if (!valid(c, xh[s]) || xh[s] == b) return fail(c, BCG_ERR_INVALID, "bad solution handle for shift %d", s);
+  if (sigma) {
+    // block_solvers.hpp:97-101 (asserts in the reference)
+    if (sigma[0] < 0.0) return fail(c, BCG_ERR_INVALID, "shifts must be zero or positive");
+    for (int s = 1; s < n_shifts; ++s)
+      if (sigma[s] < sigma[s - 1]) return fail(c, BCG_ERR_INVALID, "shifts must be in ascending order");
+  }
+  if (!c->links_set) return fail(c, BCG_ERR_INVALID, "bcg_set_links has not been called");
+  CU(cudaSetDevice(c->device));
+  int r = ensure_work(c, n_shifts);
+  if (r) return r;
+  r = init_ctrl(c, n_shifts, sigma, eps, eps_shifts, max_it);
+  if (r) return r;
+  int64_t launches = 0;
+  int l = 0;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  // X_s = 0 ; Q = B ; (Q, delta) = thinQR(Q) ; rho = delta ; P_s = Q   (block_solvers.hpp:109-117)
+  for (int s = 0; s < n_shifts; ++s) CU(cudaMemsetAsync(c->fields[xh[s]], 0, field_elems(c) * sizeof(cd), c->stream));
+  cd* Q = fptr(c, c->work_Q);
+  CU(cudaMemcpyAsync(c->fields[c->work_Q], c->fields[b], field_elems(c) * sizeof(cd), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  int np = c->ops->gram(c->stream, Q, Q, c->V, c->gpart, nullptr, c->sms, &l);
+  KL(np);
+  const cd* gsrc;
+  int nsrc;
+  r = gram_finalize(c, np, &gsrc, &nsrc, &l);
+  if (r) return r;
+  rq_init_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc, c->ctrl);
+  ++l;
+  CU(cudaGetLastError());
+  KL(c->ops->trsm(c->stream, Q, mat(c, M_DELTA), c->V, c->ctrl, c->sms, &l));
+  LoopPlan p;
+  std::memset(&p, 0, sizeof p);
+  p.kind = 1;
+  p.n_shifts = n_shifts;
+  p.T = fptr(c, c->work_T);
+  p.Q = Q;
+  p.sigma0 = sigma ? sigma[0] : 0.0;
+  for (int s = 0; s < n_shifts; ++s) {
+    CU(cudaMemcpyAsync(c->fields[c->work_P[s]], c->fields[c->work_Q], field_elems(c) * sizeof(cd),
+                       cudaMemcpyDeviceToDevice, c->stream));
+    p.fp.X[s] = fptr(c, xh[s]);
+    p.fp.P[s] = fptr(c, c->work_P[s]);
+  }
+  p.P0 = p.fp.P[0];
+  r = halo_refresh(c, p.P0, 3 * c->N, c->ctrl, &l);
+  if (r) return r;
+  launches += l;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  if (info) std::memset(info, 0, sizeof *info);
+  // while (residual > eps && iter < max_iterations), residual = 1.0 initially
+  if (1.0 > eps && max_it > 0) {
+    r = run_loop(c, p, info, &launches);
+    if (r) return r;
+  } else {
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (info) {
+      info->residual = 1.0;
+      info->n_unconverged = n_shifts;
+    }
+  }
+  return finish_info(c, info, launches);
+}
+
+int solve_bcg(bcg_ctx* c, int x, int b, double eps, int max_it, bcg_solve_info* info) {
+  if (!c) return BCG_ERR_INVALID;
+  if (!valid(c, x) || !valid(c, b) || x == b) return fail(c, BCG_ERR_INVALID, "bad field handle");
+  if (!c->links_set) return fail(c, BCG_ERR_INVALID, "bcg_set_links has not been called");
+  CU(cudaSetDevice(c->device));
+  int r = ensure_work(c, 1);
+  if (r) return r;
+  r = init_ctrl(c, 1, nullptr, eps, 0.0, max_it);
+  if (r) return r;
+  int64_t launches = 0;
+  int l = 0;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  // X = 0 ; P = R = B ; r2 = R^dag R   (block_solvers.hpp:13-22)
+  CU(cudaMemsetAsync(c->fields[x], 0, field_elems(c) * sizeof(cd), c->stream));
+  CU(cudaMemcpyAsync(c->fields[c->work_Q], c->fields[b], field_elems(c) * sizeof(cd), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  CU(cudaMemcpyAsync(c->fields[c->work_P[0]], c->fields[b], field_elems(c) * sizeof(cd), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  cd* R = fptr(c, c->work_Q);
+  int np = c->ops->gram(c->stream, R, R, c->V, c->gpart, nullptr, c->sms, &l);
+  KL(np);
+  const cd* gsrc;
+  int nsrc;
+  r = gram_finalize(c, np, &gsrc, &nsrc, &l);
+  if (r) return r;
+  bcg_init_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc);
+  ++l;
+  CU(cudaGetLastError());
+  LoopPlan p;
+  std::memset(&p, 0, sizeof p);
+  p.kind = 0;
+  p.n_shifts = 1;
+  p.T = fptr(c, c->work_T);
+  p.Q = R;
+  p.sigma0 = 0.0;
+  p.fp.X[0] = fptr(c, x);
+  p.fp.P[0] = fptr(c, c->work_P[0]);
+  p.P0 = p.fp.P[0];
+  r = halo_refresh(c, p.P0, 3 * c->N, c->ctrl, &l);
+  if (r) return r;
+  launches += l;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  if (info) std::memset(info, 0, sizeof *info);
+  if (1.0 > eps && max_it > 0) {
+    r = run_loop(c, p, info, &launches);
+    if (r) return r;
+  } else {
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (info) info->residual = 1.0;
+  }
+  return finish_info(c, info, launches);
+}
+
+int ensure_host_handles(bcg_ctx* c, int n_shifts) {
+  if (c->host_B < 0) {
+    int r = field_alloc(c, &c->host_B);
+    if (r) return r;
+  }
+  while (static_cast<int>(c->host_X.size()) < n_shifts) {
+    int h;
+    int r = field_alloc(c, &h);
+    if (r) return r;
+    c->host_X.push_back(h);
+  }
+  return BCG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bcg_solve_bcg_dev(bcg_ctx* c, int x, int b, double eps, int max_it, bcg_solve_info* info) {
+  return solve_bcg(c, x, b, eps, max_it, info);
+}
+int bcg_solve_bcgrq_dev(bcg_ctx* c, int x, int b, double eps, int max_it, bcg_solve_info* info) {
+  // BCGrQ == SBCGrQ with the single shift 0 (block_solvers.hpp:50-86 vs 91-185)
+  const double zero = 0.0;
+  return solve_rq(c, &x, b, &zero, 1, eps, 0.0, max_it, info);
+}
+int bcg_solve_sbcgrq_dev(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts, double eps,
+                         double eps_shifts, int max_it, bcg_solve_info* info) {
+  if (!sigma) return fail(c, BCG_ERR_INVALID, "sigma is null");
+  return solve_rq(c, xh, b, sigma, n_shifts, eps, eps_shifts, max_it, info);
+}
+
+int bcg_solve_bcg(bcg_ctx* c, double* x_host, const double* b_host, double eps, int max_it, bcg_solve_info* info) {
+  if (!c || !x_host || !b_host) return fail(c, BCG_ERR_INVALID, "null argument");
+  int r = ensure_host_handles(c, 1);
+  if (r) return r;
+  if ((r = bcg_field_upload(c, c->host_B, b_host))) return r;
+  if ((r = solve_bcg(c, c->host_X[0], c->host_B, eps, max_it, info))) return r;
+  return bcg_field_download(c, c->host_X[0], x_host);
+}
+int bcg_solve_bcgrq(bcg_ctx* c, double* x_host, const double* b_host, double eps, int max_it,
+                    bcg_solve_info* info) {
+  if (!c || !x_host || !b_host) return fail(c, BCG_ERR_INVALID, "null argument");
+  int r = ensure_host_handles(c, 1);
+  if (r) return r;
+  if ((r = bcg_field_upload(c, c->host_B, b_host))) return r;
+  if ((r = bcg_solve_bcgrq_dev(c, c->host_X[0], c->host_B, eps, max_it, info))) return r;
+  return bcg_field_download(c, c->host_X[0], x_host);
+}
+int bcg_solve_sbcgrq(bcg_ctx* c, double* const* x_host, const double* b_host, const double* sigma, int n_shifts,
+                     double eps, double eps_shifts, int max_it, bcg_solve_info* info) {
+  if (!c || !x_host || !b_host || !sigma) return fail(c, BCG_ERR_INVALID, "null argument");
+  if (n_shifts < 1 || n_shifts > c->S) return fail(c, BCG_ERR_INVALID, "bad n_shifts=%d (context max %d)", n_shifts, c->S);
+  int r = ensure_host_handles(c, n_shifts);
+  if (r) return r;
+  if ((r = bcg_field_upload(c, c->host_B, b_host))) return r;
+  if ((r = bcg_solve_sbcgrq_dev(c, c->host_X.data(), c->host_B, sigma, n_shifts, eps, eps_shifts, max_it, info)))
+    return r;
+  for (int s = 0; s < n_shifts; ++s)
+    if ((r = bcg_field_download(c, c->host_X[s], x_host[s]))) return r;
+  return BCG_OK;
+}
+
+// ---- micro-benchmark hook ----------------------------------------------------------------------
+int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h, int nh, double* ms_out,
+                     int64_t* launches_out) {
+  if (!c || !ms_out || reps < 1) return fail(c, BCG_ERR_INVALID, "bad argument to bench_kernel");
+  for (int i = 0; i < nh; ++i)
+    if (!valid(c, h[i])) return fail(c, BCG_ERR_INVALID, "bad handle");
+  if (!c->links_set) return fail(c, BCG_ERR_INVALID, "bcg_set_links has not been called");
+  CU(cudaSetDevice(c->device));
+  int launches = 0;
+  const double m2 = c->mass * c->mass;
+  ShiftPtrs fp;
+  std::memset(&fp, 0, sizeof fp);
+  if (which == 4) {
+    if (nh < 1 + 2 * n_shifts || n_shifts < 1 || n_shifts > c->S) return fail(c, BCG_ERR_INVALID, "need 1+2S handles");
+    for (int s = 0; s < n_shifts; ++s) {
+      fp.X[s] = fptr(c, h[1 + 2 * s]);
+      fp.P[s] = fptr(c, h[2 + 2 * s]);
+    }
+  } else if (nh < 2) {
+    return fail(c, BCG_ERR_INVALID, "need 2 handles");
+  }
+  auto body = [&](int* l) -> int {
+    switch (which) {
+      case 0:
+        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, c->gpart, nullptr, c->sms, l));
+        break;
+      case 1:
+        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, nullptr, nullptr, c->sms, l));
+        break;
+      case 2:
+        KL(c->ops->gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), c->V, c->gpart, nullptr, c->sms, l));
+        break;
+      case 3:
+        KL(c->ops->axpy_gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, c->gpart, nullptr,
+                             c->sms, l));
+        break;
+      case 4:
+        KL(c->ops->shift_update(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
+                                c->mats + c->L.B(0), c->V, 1, n_shifts, nullptr, c->sms, l));
+        break;
+      case 5:
+        KL(c->ops->axpy_gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, nullptr, nullptr,
+                             c->sms, l));
+        break;
+      case 6:
+        KL(c->ops->rescale_add(c->stream, fptr(c, h[0]), mat(c, M_SCRATCH), fptr(c, h[1]), 1.0, c->V, c->sms, l));
+        break;
+      default:
+        return fail(c, BCG_ERR_INVALID, "unknown kernel id %d", which);
+    }
+    return BCG_OK;
+  };
+  // coefficient operands that keep the data bounded over many repetitions:
+  // identity-like upper-triangular R, tiny A/B
+  {
+    const size_t nn = c->L.nn();
+    std::vector<cd> I(nn, make_double2(0, 0)), Z(nn, make_double2(0, 0));
+    for (int i = 0; i < c->N; ++i) I[i + c->N * i] = make_double2(1.0, 0.0);
+    for (size_t e = 0; e < nn; ++e) Z[e] = make_double2(1e-3 * ((e * 7) % 5), -1e-3 * ((e * 3) % 7));
+    CU(cudaMemcpy(mat(c, M_SCRATCH), which == 4 ? I.data() : Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+    for (int s = 0; s < c->S; ++s) {
+      CU(cudaMemcpy(c->mats + c->L.A(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(c->mats + c->L.B(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+    }
+  }
+  int dummy = 0;
+  for (int w = 0; w < 3; ++w) {
+    int r = body(&dummy);
+    if (r) return r;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  for (int i = 0; i < reps; ++i) {
+    int r = body(&launches);
+    if (r) return r;
+  }
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  *ms_out = ms / reps;
+  if (launches_out) *launches_out = launches;
+  return BCG_OK;
+}
+
+}  // extern "C"

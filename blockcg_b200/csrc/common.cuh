@@ -1,0 +1,136 @@
+// Shared device-side definitions for the block-CG kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bcg {
+
+typedef double2 cd;  // complex128: x = re, y = im
+
+constexpr int kMaxShifts = 32;
+constexpr int kNc = 3;  // colours (N_f in the reference, inc/fields.hpp:18)
+
+// ---- complex helpers (each cmac = 4 DFMA) -----------------------------------------
+__device__ __forceinline__ cd cmake(double re, double im) { return make_double2(re, im); }
+__device__ __forceinline__ cd czero() { return make_double2(0.0, 0.0); }
+__device__ __forceinline__ cd cconj(cd a) { return make_double2(a.x, -a.y); }
+__device__ __forceinline__ cd cadd(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cd csub(cd a, cd b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cd cmul(cd a, cd b) {
+  return make_double2(fma(-a.y, b.y, a.x * b.x), fma(a.y, b.x, a.x * b.y));
+}
+__device__ __forceinline__ cd cscale(cd a, double s) { return make_double2(a.x * s, a.y * s); }
+// acc += a*b
+__device__ __forceinline__ void cmac(cd& acc, cd a, cd b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+// acc -= a*b
+__device__ __forceinline__ void cmsub(cd& acc, cd a, cd b) {
+  acc.x = fma(-a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(-a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc += conj(a)*b
+__device__ __forceinline__ void cmac_conj(cd& acc, cd a, cd b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double cabs2(cd a) { return fma(a.x, a.x, a.y * a.y); }
+__device__ __forceinline__ cd cdiv(cd a, cd b) {
+  // scaled division (robust against over/underflow of |b|^2)
+  double s = fmax(fabs(b.x), fabs(b.y));
+  double br = b.x / s, bi = b.y / s;
+  double d = (br * br + bi * bi) * s;
+  return make_double2((a.x * br + a.y * bi) / d, (a.y * br - a.x * bi) / d);
+}
+
+// ---- loop control block living in device memory -------------------------------------
+// The iteration loop never round-trips to the host: every kernel of an
+// iteration looks at `done` (and the stencil at `stop`) and returns early, so
+// the host can enqueue batches of iterations blindly and poll a pinned mirror.
+struct Ctrl {
+  int iter;       // operator applications so far (the reference's return value)
+  int stop;       // set by the B-step of the last iteration; the iteration still completes
+  int done;       // loop finished: all later kernels are no-ops
+  int n_unconv;   // shifts still being updated (block_solvers.hpp:104,179-181)
+  int status;     // bcg_status raised on device (not-PD Gram, NaN)
+  int max_it;
+  int n_shifts;
+  int pad0;
+  double eps;
+  double eps_shifts;
+  double residual;
+  int conv[kMaxShifts];            // shift converged in the current iteration
+  double resid_shift[kMaxShifts];  // last shifted residual estimate
+  double sigma[kMaxShifts];
+};
+
+// ---- mbarrier + 1-D bulk TMA (cp.async.bulk) ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global, tracked by a bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy smem writes visible to the async proxy (before a bulk store)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Shared-memory operand load that the high-level optimiser may not hoist out of
+// the row loops (LICM of a whole N x N coefficient matrix into registers is a
+// guaranteed spill); ptxas still schedules it freely.
+__device__ __forceinline__ cd lds_cd(const cd* p) {
+  cd r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(smem_u32(p)));
+  return r;
+}
+
+// streaming global access (fields are touched once per kernel)
+__device__ __forceinline__ cd ldg_stream(const cd* p) {
+  cd r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+}  // namespace bcg

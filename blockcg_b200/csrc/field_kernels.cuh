@@ -1,0 +1,612 @@
+// Field-sized kernels of the block-CG hot path, templated on N (= N_rhs).
+//
+// Layout (the reference's, inc/fields.hpp:18-30): field[x][r][c], complex128,
+// c fastest; element (x, r, c) at complex index (x*N + r)*3 + c.  Device
+// fields carry a 2-site halo on both ends (pointer = site 0), links likewise
+// (element (i,j) of U[x] at x*9 + i + 3*j).
+//
+//  K1 dirac_kernel      T = (m^2 + sigma) P - D(D(P))  [+ partial Gram P^dag T]
+//  K2 gram_kernel       partial Gram A^dag B
+//  K3 axpy_gram_kernel  Q += T*M  [+ partial Gram Q^dag Q]
+//  K4 shift_update_kernel  Q <- Q rho^-1 ; for every active shift s:
+//                          X_s += P_s A_s ;  P_s <- P_s B_s + Q
+//  plus the stand-alone primitives (add, rescale_add, trsm, halo wrap ...).
+//
+// Partial Grams: one N x N block per CTA, reduced in a fixed order by the
+// small-matrix kernels (no floating-point atomics anywhere => bitwise
+// reproducible run to run).
+#pragma once
+#include "common.cuh"
+
+namespace bcg {
+
+// ------------------------------------------------------------------------------------
+// Gram building block: a warp accumulates one 4x4 block (ti,tj) of A^dag B over
+// rows (site,colour) of two shared-memory tiles.  acc[ii][jj] += conj(a_ii) b_jj.
+// ------------------------------------------------------------------------------------
+template <int N>
+struct GramGeom {
+  static constexpr int NB = (N + 3) / 4;             // 4-wide blocks per dimension
+  static constexpr int NTASK = NB * (NB + 1) / 2;    // lower-triangular blocks
+};
+
+__device__ __forceinline__ void gram_task_to_block(int t, int& ti, int& tj) {
+  // t = ti*(ti+1)/2 + tj, tj <= ti
+  ti = 0;
+  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+  tj = t - ti * (ti + 1) / 2;
+}
+
+template <int N>
+__device__ __forceinline__ void gram_rows(const cd* __restrict__ sA, const cd* __restrict__ sB, int nrows,
+                                          int ti, int tj, int row0, int rowstep, cd (&acc)[4][4]) {
+  for (int row = row0; row < nrows; row += rowstep) {
+    const int site = row / 3;
+    const int base = site * (3 * N) + (row - 3 * site);
+    cd a[4], b[4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int ka = 4 * ti + ii, kb = 4 * tj + ii;
+      a[ii] = (N % 4 == 0 || ka < N) ? sA[base + 3 * ka] : czero();
+      b[ii] = (N % 4 == 0 || kb < N) ? sB[base + 3 * kb] : czero();
+    }
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) cmac_conj(acc[ii][jj], a[ii], b[jj]);
+  }
+}
+
+// Reduce a warp's 4x4 accumulator over lanes (fixed xor tree) and let lane 0
+// store it into an N x N column-major block (entries outside the matrix skipped).
+template <int N>
+__device__ __forceinline__ void gram_warp_store(cd (&acc)[4][4], int ti, int tj, cd* dstNN, bool accumulate) {
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      double re = acc[ii][jj].x, im = acc[ii][jj].y;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, off);
+        im += __shfl_xor_sync(0xffffffffu, im, off);
+      }
+      const int i = 4 * ti + ii, j = 4 * tj + jj;
+      if ((threadIdx.x & 31) == 0 && i < N && j < N) {
+        cd* d = dstNN + i + N * j;
+        if (accumulate) {
+          d->x += re;
+          d->y += im;
+        } else {
+          *d = cmake(re, im);
+        }
+      }
+    }
+}
+
+// CTA-level Gram bookkeeping shared by K1/K2/K3.  NW warps; warp w owns task
+// (w % NTASK) and row slice (w / NTASK) of NSLICE = NW / NTASK (>= 1 required).
+template <int N, int NW>
+struct GramCta {
+  static constexpr int NTASK = GramGeom<N>::NTASK;
+  static constexpr int NSLICE = NW / NTASK;
+  static_assert(NSLICE >= 1, "not enough warps for the fused Gram at this N");
+  static constexpr int NACTIVE = NSLICE * NTASK;  // warps that take part
+
+  int ti, tj, slice;
+  bool active;
+  cd acc[4][4];
+
+  __device__ __forceinline__ void init() {
+    const int w = threadIdx.x >> 5;
+    active = w < NACTIVE;
+    const int t = w % NTASK;
+    slice = w / NTASK;
+    gram_task_to_block(t, ti, tj);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = czero();
+  }
+  __device__ __forceinline__ void accumulate(const cd* sA, const cd* sB, int nrows) {
+    if (active) gram_rows<N>(sA, sB, nrows, ti, tj, slice * 32 + (threadIdx.x & 31), NSLICE * 32, acc);
+  }
+  // sG: shared scratch of NSLICE * N*N complex.  Writes the CTA's partial
+  // (lower-triangular blocks valid) to gpart[N*N].
+  __device__ __forceinline__ void finish(cd* sG, cd* __restrict__ gpart) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < NSLICE * N * N; e += blockDim.x) sG[e] = czero();
+    __syncthreads();
+    if (active) gram_warp_store<N>(acc, ti, tj, sG + slice * N * N, false);
+    __syncthreads();
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+      cd s = sG[e];
+#pragma unroll
+      for (int sl = 1; sl < NSLICE; ++sl) s = cadd(s, sG[sl * N * N + e]);
+      gpart[e] = s;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// K1: block Dirac apply.  1-D chain operator of the reference
+// (inc/dirac_op.hpp:14-21,36-43): D v[x] = 1/2 U[x] v[x+1] - 1/2 U[x-1]^dag v[x-1],
+// out = m^2 v - D(D v) (+ sigma v, block_solvers.hpp:136), both sweeps in one
+// kernel with the intermediate in shared memory.  Each link is fetched once per
+// CTA tile and reused for all N right-hand sides.
+//
+// Work item = (site, group of R rhs columns): thread keeps R*3 accumulators.
+// ------------------------------------------------------------------------------------
+template <int N, int R>
+__device__ __forceinline__ void load_cols(const cd* __restrict__ s, cd (&v)[R][3]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[r][c] = s[r * 3 + c];
+}
+
+// acc[r][i] += sum_j U(i,j) v[r][j]
+template <int R>
+__device__ __forceinline__ void apply_link(const cd* __restrict__ sU, const cd (&v)[R][3], cd (&acc)[R][3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const cd u = sU[i + 3 * j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) cmac(acc[r][i], u, v[r][j]);
+    }
+}
+// acc[r][i] -= sum_j conj(U(j,i)) v[r][j]
+template <int R>
+__device__ __forceinline__ void apply_link_dag_sub(const cd* __restrict__ sU, const cd (&v)[R][3],
+                                                   cd (&acc)[R][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const cd u = cconj(sU[j + 3 * i]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) cmsub(acc[r][i], u, v[r][j]);
+    }
+}
+
+template <int N, int R, int NT>
+struct DiracGeom {
+  static_assert(N % R == 0, "R must divide N");
+  static constexpr int G = N / R;           // work items per site
+  static constexpr int TS1 = NT / G;        // sites covered by the first sweep
+  static constexpr int TS = TS1 - 2;        // output sites per tile
+  static_assert(TS >= 1, "block too small for this N/R");
+  static constexpr int SITE = 3 * N;        // complex per site
+  static constexpr int IN_ELEMS = (TS + 4) * SITE;
+  static constexpr int TMP_ELEMS = (TS + 2) * SITE;
+  static constexpr int OUT_ELEMS = TS * SITE;
+  static constexpr int U_ELEMS = (TS + 3) * 9;
+  static constexpr int NW = NT / 32;
+  static constexpr bool CAN_GRAM = (NW >= GramGeom<N>::NTASK);
+  static constexpr int GRAM_ELEMS = CAN_GRAM ? (NW / GramGeom<N>::NTASK) * N * N : 0;
+  static constexpr size_t SMEM_BYTES =
+      sizeof(cd) * (IN_ELEMS + TMP_ELEMS + OUT_ELEMS + U_ELEMS + GRAM_ELEMS) + 16;
+};
+
+template <int N, int R, int NT, bool GRAM>
+__global__ void __launch_bounds__(NT)
+dirac_kernel(const cd* __restrict__ in, cd* __restrict__ out, const cd* __restrict__ U, long long V,
+             double m2, double sigma, cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl) {
+  using Geo = DiracGeom<N, R, NT>;
+  constexpr int G = Geo::G, TS = Geo::TS, SITE = Geo::SITE;
+  if (ctrl != nullptr && (ctrl->done | ctrl->stop)) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cd* sIn = reinterpret_cast<cd*>(smem_raw);
+  cd* sTmp = sIn + Geo::IN_ELEMS;
+  cd* sOut = sTmp + Geo::TMP_ELEMS;
+  cd* sU = sOut + Geo::OUT_ELEMS;
+  cd* sG = sU + Geo::U_ELEMS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sG + Geo::GRAM_ELEMS);
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  GramCta<N, GRAM ? Geo::NW : GramGeom<N>::NTASK> gram;  // dummy geometry when !GRAM
+  if (GRAM) gram.init();
+
+  const long long ntiles = (V + TS - 1) / TS;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long x0 = tile * TS;
+    const int ns = static_cast<int>(min(static_cast<long long>(TS), V - x0));
+    // ---- stage P[x0-2 .. x0+ns+2) and U[x0-2 .. x0+ns+1) with two bulk copies ----
+    if (tid == 0) {
+      const uint32_t bytes_in = static_cast<uint32_t>((ns + 4) * SITE * sizeof(cd));
+      const uint32_t bytes_u = static_cast<uint32_t>((ns + 3) * 9 * sizeof(cd));
+      mbar_arrive_expect_tx(bar, bytes_in + bytes_u);
+      bulk_g2s(sIn, in + (x0 - 2) * SITE, bytes_in, bar);
+      bulk_g2s(sU, U + (x0 - 2) * 9, bytes_u, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+
+    // ---- sweep 1: tmp[y] for y = x0-1 .. x0+ns   (local ls = 0 .. ns+1) ----
+    for (int item = tid; item < (ns + 2) * G; item += NT) {
+      const int ls = item / G, g = item - ls * G;
+      cd v[R][3], acc[R][3];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[r][c] = czero();
+      load_cols<N, R>(sIn + (ls + 2) * SITE + g * R * 3, v);  // P[y+1]
+      apply_link<R>(sU + (ls + 1) * 9, v, acc);               // U[y]
+      load_cols<N, R>(sIn + ls * SITE + g * R * 3, v);        // P[y-1]
+      apply_link_dag_sub<R>(sU + ls * 9, v, acc);             // U[y-1]^dag
+      cd* t = sTmp + ls * SITE + g * R * 3;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) t[r * 3 + c] = cscale(acc[r][c], 0.5);
+    }
+    if (tid == 0) bulk_wait_read0();  // previous tile's bulk store has drained sOut
+    __syncthreads();
+
+    // ---- sweep 2 + mass/shift term: out[x] for x = x0 .. x0+ns-1 ----
+    for (int item = tid; item < ns * G; item += NT) {
+      const int ls = item / G, g = item - ls * G;
+      cd v[R][3], acc[R][3];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[r][c] = czero();
+      load_cols<N, R>(sTmp + (ls + 2) * SITE + g * R * 3, v);  // tmp[x+1]
+      apply_link<R>(sU + (ls + 2) * 9, v, acc);                // U[x]
+      load_cols<N, R>(sTmp + ls * SITE + g * R * 3, v);        // tmp[x-1]
+      apply_link_dag_sub<R>(sU + (ls + 1) * 9, v, acc);        // U[x-1]^dag
+      load_cols<N, R>(sIn + (ls + 2) * SITE + g * R * 3, v);   // P[x]
+      cd* o = sOut + ls * SITE + g * R * 3;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          // lhs = -D(D rhs) + m^2 rhs   (dirac_op.hpp:42), then += sigma rhs
+          cd t = cmake(fma(m2, v[r][c].x, -0.5 * acc[r][c].x), fma(m2, v[r][c].y, -0.5 * acc[r][c].y));
+          t.x = fma(sigma, v[r][c].x, t.x);
+          t.y = fma(sigma, v[r][c].y, t.y);
+          o[r * 3 + c] = t;
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(out + x0 * SITE, sOut, static_cast<uint32_t>(ns * SITE * sizeof(cd)));
+      bulk_commit();
+    }
+    // ---- fused Gram epilogue: P^dag T over this tile's rows ----
+    if (GRAM) {
+      gram.accumulate(sIn + 2 * SITE, sOut, 3 * ns);
+    }
+    __syncthreads();  // tile buffers free for the next round
+  }
+  if (tid == 0) bulk_wait0();
+  if (GRAM) gram.finish(sG, gpart + static_cast<size_t>(blockIdx.x) * N * N);
+}
+
+// ------------------------------------------------------------------------------------
+// K2: stand-alone partial Gram A^dag B.  blockIdx.y selects a group of NW tasks
+// (one 4x4 block per warp) so any N fits; tiles are staged by bulk copies.
+// gpart[blockIdx.x][N*N]; blocks of different y write disjoint entries.
+// ------------------------------------------------------------------------------------
+template <int N, int NT>
+struct GramKGeom {
+  static constexpr int TS = 32;
+  static constexpr int SITE = 3 * N;
+  static constexpr size_t SMEM_BYTES = sizeof(cd) * (2 * TS * SITE) + 16;
+};
+
+template <int N, int NT>
+__global__ void __launch_bounds__(NT)
+gram_kernel(const cd* __restrict__ A, const cd* __restrict__ B, long long V, cd* __restrict__ gpart,
+            const Ctrl* __restrict__ ctrl) {
+  using Geo = GramKGeom<N, NT>;
+  constexpr int TS = Geo::TS, SITE = Geo::SITE, NW = NT / 32;
+  constexpr int NTASK = GramGeom<N>::NTASK;
+  if (ctrl != nullptr && ctrl->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cd* sA = reinterpret_cast<cd*>(smem_raw);
+  cd* sB = sA + TS * SITE;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + TS * SITE);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const bool same = (A == B);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int task = blockIdx.y * NW + w;
+  const bool active = task < NTASK;
+  int ti = 0, tj = 0;
+  if (active) gram_task_to_block(task, ti, tj);
+  cd acc[4][4];
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = czero();
+
+  const long long ntiles = (V + TS - 1) / TS;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long x0 = tile * TS;
+    const int ns = static_cast<int>(min(static_cast<long long>(TS), V - x0));
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(ns * SITE * sizeof(cd));
+      mbar_arrive_expect_tx(bar, same ? bytes : 2 * bytes);
+      bulk_g2s(sA, A + x0 * SITE, bytes, bar);
+      if (!same) bulk_g2s(sB, B + x0 * SITE, bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    if (active) gram_rows<N>(sA, same ? sA : sB, 3 * ns, ti, tj, lane, 32, acc);
+    __syncthreads();
+  }
+  if (active) gram_warp_store<N>(acc, ti, tj, gpart + static_cast<size_t>(blockIdx.x) * N * N, false);
+}
+
+// ------------------------------------------------------------------------------------
+// Row helpers: one thread owns one (site, colour) row of N complex numbers,
+// element k at stride 3.  out[j] (+)= sum_k p[k] M(k,j), M column-major in smem.
+// ------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void row_load(const cd* __restrict__ f, long long row_base, cd (&r)[N]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) r[k] = f[row_base + 3 * k];
+}
+template <int N>
+__device__ __forceinline__ void row_store(cd* __restrict__ f, long long row_base, const cd (&r)[N]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) f[row_base + 3 * k] = r[k];
+}
+template <int N>
+__device__ __forceinline__ void row_mm_acc(cd (&out)[N], const cd (&p)[N], const cd* __restrict__ sM) {
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int k = 0; k < N; ++k) cmac(out[j], p[k], lds_cd(sM + k + N * j));
+}
+__device__ __forceinline__ long long row_base_of(long long row, int N) {
+  const long long site = row / 3;
+  return site * (3 * N) + (row - 3 * site);
+}
+
+// K3: Q += T*M with the partial Gram Q^dag Q of the updated rows fused in.
+// CTA tile = NT rows = NT/3 sites (NT % 3 == 0); updated rows are staged in
+// shared memory for the Gram warps.
+template <int N, int NT>
+struct AxpyGeom {
+  static_assert(NT % 3 == 0, "block must hold whole sites");
+  static constexpr int TS = NT / 3;
+  static constexpr int NW = NT / 32;
+  static constexpr bool CAN_GRAM = (NW >= GramGeom<N>::NTASK);
+  static constexpr int GRAM_ELEMS = CAN_GRAM ? (NW / GramGeom<N>::NTASK) * N * N : 0;
+  static constexpr size_t SMEM_BYTES = sizeof(cd) * (N * N + (CAN_GRAM ? TS * 3 * N : 0) + GRAM_ELEMS);
+};
+
+template <int N, int NT, bool GRAM>
+__global__ void __launch_bounds__(NT)
+axpy_gram_kernel(cd* __restrict__ Q, const cd* __restrict__ T, const cd* __restrict__ M, long long V,
+                 cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl) {
+  using Geo = AxpyGeom<N, NT>;
+  if (ctrl != nullptr && ctrl->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cd* sM = reinterpret_cast<cd*>(smem_raw);
+  cd* sQ = sM + N * N;
+  cd* sG = sQ + (GRAM ? Geo::TS * 3 * N : 0);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < N * N; e += NT) sM[e] = M[e];
+  GramCta<N, GRAM ? Geo::NW : GramGeom<N>::NTASK> gram;
+  if (GRAM) gram.init();
+  __syncthreads();
+  const long long nrows = 3 * V;
+  const long long ntiles = (nrows + NT - 1) / NT;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * NT + tid;
+    const int rows_here = static_cast<int>(min(static_cast<long long>(NT), nrows - tile * NT));
+    if (row < nrows) {
+      const long long rb = row_base_of(row, N);
+      cd t[N], q[N];
+      row_load<N>(T, rb, t);
+      row_load<N>(Q, rb, q);
+      row_mm_acc<N>(q, t, sM);
+      row_store<N>(Q, rb, q);
+      if (GRAM) {
+        const int lb = (tid / 3) * (3 * N) + (tid % 3);
+#pragma unroll
+        for (int k = 0; k < N; ++k) sQ[lb + 3 * k] = q[k];
+      }
+    }
+    if (GRAM) {
+      __syncthreads();
+      gram.accumulate(sQ, sQ, rows_here);
+      __syncthreads();
+    }
+  }
+  if (GRAM) gram.finish(sG, gpart + static_cast<size_t>(blockIdx.x) * N * N);
+}
+
+// dst = dst*L + r*src  (fields.hpp:79-90);  with L == nullptr: dst += src*Madd (fields.hpp:70-77)
+template <int N, int NT>
+__global__ void __launch_bounds__(NT)
+rescale_add_kernel(cd* __restrict__ dst, const cd* __restrict__ L, const cd* __restrict__ src, double r,
+                   long long V) {
+  __shared__ cd sM[N * N];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < N * N; e += NT) sM[e] = L[e];
+  __syncthreads();
+  const long long nrows = 3 * V;
+  for (long long row = static_cast<long long>(blockIdx.x) * NT + tid; row < nrows;
+       row += static_cast<long long>(gridDim.x) * NT) {
+    const long long rb = row_base_of(row, N);
+    cd d[N], s[N], o[N];
+    row_load<N>(dst, rb, d);
+    row_load<N>(src, rb, s);
+#pragma unroll
+    for (int j = 0; j < N; ++j) o[j] = czero();
+    row_mm_acc<N>(o, d, sM);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      o[j].x = fma(s[j].x, r, o[j].x);
+      o[j].y = fma(s[j].y, r, o[j].y);
+    }
+    row_store<N>(dst, rb, o);
+  }
+}
+
+// dst += s*src, element-wise (block_solvers.hpp:136) ; also plain copies / sets
+static __global__ void axpy_scalar_kernel(cd* __restrict__ dst, const cd* __restrict__ src, double s, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    cd d = dst[i], v = src[i];
+    d.x = fma(v.x, s, d.x);
+    d.y = fma(v.y, s, d.y);
+    dst[i] = d;
+  }
+}
+// dst = a - b (verification: AX -= B)
+static __global__ void sub_kernel(cd* dst, const cd* a, const cd* __restrict__ b, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = csub(a[i], b[i]);
+}
+
+// In-register back substitution of one row: q <- q R^-1 in the reference's
+// column order (fields.hpp:125-136); R upper triangular, column-major in smem.
+template <int N>
+__device__ __forceinline__ void row_backsub(cd (&q)[N], const cd* __restrict__ sR) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) cmsub(q[i], lds_cd(sR + j + N * i), q[j]);
+    q[i] = cdiv(q[i], lds_cd(sR + i + N * i));
+  }
+}
+
+template <int N, int NT>
+__global__ void __launch_bounds__(NT)
+trsm_kernel(cd* __restrict__ Q, const cd* __restrict__ Rm, long long V, const Ctrl* __restrict__ ctrl) {
+  if (ctrl != nullptr && ctrl->done) return;
+  __shared__ cd sR[N * N];
+  const int tid = threadIdx.x;
+  for (int e = tid; e < N * N; e += NT) sR[e] = Rm[e];
+  __syncthreads();
+  const long long nrows = 3 * V;
+  for (long long row = static_cast<long long>(blockIdx.x) * NT + tid; row < nrows;
+       row += static_cast<long long>(gridDim.x) * NT) {
+    const long long rb = row_base_of(row, N);
+    cd q[N];
+    row_load<N>(Q, rb, q);
+    row_backsub<N>(q, sR);
+    row_store<N>(Q, rb, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K4: the multishift update, one streaming pass over 2 + 4*S_active fields:
+//   Q  <- Q rho^-1                                (thinQR back substitution)
+//   X_s += P_s A_s ;  P_s <- P_s B_s + Q          for s = 0 .. n_active-1
+// with A_0 = alpha*delta_old, B_0 = rho^dag, A_s = alpha_s, B_s = beta_s rho^dag
+// (block_solvers.hpp:145,152,158,175,177).  Q is read once and kept in
+// registers across all shifts.  n_active is read from the control block, so
+// converged shifts drop out without host involvement.
+// With do_backsub == 0 the kernel is the BCG update (X += P A; P <- P B + R).
+// ------------------------------------------------------------------------------------
+struct ShiftPtrs {
+  cd* X[kMaxShifts];
+  cd* P[kMaxShifts];
+};
+
+template <int N, int NT>
+__global__ void __launch_bounds__(NT)
+shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
+                    const cd* __restrict__ Amats, const cd* __restrict__ Bmats, long long V,
+                    int do_backsub, int n_active_fixed, const Ctrl* __restrict__ ctrl) {
+  if (ctrl != nullptr && ctrl->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cd* sR = reinterpret_cast<cd*>(smem_raw);
+  cd* sA[2] = {sR + N * N, sR + 2 * N * N};
+  cd* sB[2] = {sR + 3 * N * N, sR + 4 * N * N};
+  const int tid = threadIdx.x;
+  const int n_active = (n_active_fixed > 0) ? n_active_fixed : ctrl->n_unconv;
+  if (do_backsub)
+    for (int e = tid; e < N * N; e += NT) sR[e] = Rm[e];
+  const long long nrows = 3 * V;
+  const long long ntiles = (nrows + NT - 1) / NT;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row = tile * NT + tid;
+    const bool live = row < nrows;
+    const long long rb = live ? row_base_of(row, N) : 0;
+    cd q[N];
+    for (int s = 0; s < n_active; ++s) {
+      const int buf = s & 1;
+      for (int e = tid; e < N * N; e += NT) {
+        sA[buf][e] = Amats[static_cast<size_t>(s) * N * N + e];
+        sB[buf][e] = Bmats[static_cast<size_t>(s) * N * N + e];
+      }
+      __syncthreads();
+      if (live) {
+        if (s == 0) {
+          row_load<N>(Q, rb, q);
+          if (do_backsub) {
+            row_backsub<N>(q, sR);
+            row_store<N>(Q, rb, q);
+          }
+        }
+        cd p[N];
+        row_load<N>(fp.P[s], rb, p);
+        {
+          cd x[N];
+          row_load<N>(fp.X[s], rb, x);
+          row_mm_acc<N>(x, p, sA[buf]);
+          row_store<N>(fp.X[s], rb, x);
+        }
+        {
+          cd pn[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) pn[j] = czero();
+          row_mm_acc<N>(pn, p, sB[buf]);
+#pragma unroll
+          for (int j = 0; j < N; ++j) pn[j] = cadd(pn[j], q[j]);  // tmp = P*L ; tmp += Q*1.0 (fields.hpp:85-86)
+          row_store<N>(fp.P[s], rb, pn);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Halo refresh for one rank: slots -2,-1,V,V+1 <- periodic images (any V >= 1).
+// `site` = complex numbers per site (3N for fields, 9 for links).
+static __global__ void halo_wrap_kernel(cd* __restrict__ f, long long V, int site, const Ctrl* __restrict__ ctrl) {
+  if (ctrl != nullptr && ctrl->done) return;
+  const int n = 4 * site;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int slot = i / site, e = i - slot * site;
+    const long long h = (slot < 2) ? (slot - 2) : (V + slot - 2);
+    long long src = h % V;
+    if (src < 0) src += V;
+    f[h * site + e] = f[src * site + e];
+  }
+}
+
+// pack the two boundary slabs (first 2 / last 2 sites) for a neighbour exchange
+static __global__ void halo_pack_kernel(const cd* __restrict__ f, long long V, int site, cd* __restrict__ send_lo,
+                                 cd* __restrict__ send_hi) {
+  const int n = 2 * site;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    send_lo[i] = f[i];                    // sites 0,1   -> left neighbour's slots V, V+1
+    send_hi[i] = f[(V - 2) * site + i];   // sites V-2,V-1 -> right neighbour's slots -2,-1
+  }
+}
+
+}  // namespace bcg

@@ -1,0 +1,194 @@
+// Host-side launchers, one table per compiled N (see inst.cu / registry in capi.cu).
+#pragma once
+#include "common.cuh"
+#include "field_kernels.cuh"
+
+namespace bcg {
+
+struct OpsTable {
+  int N;
+  int dirac_rhs_per_thread;
+  int dirac_tile_sites;
+  int fused_gram;  // 1 if the Gram epilogue is fused into K1/K3 at this N
+  // Each launcher returns the number of partial Gram blocks it produced (0 if none),
+  // or a negative cudaError_t.
+  int (*dirac)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
+               cd* gpart, const Ctrl* ctrl, int sms, int* launches);
+  int (*gram)(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
+              int* launches);
+  int (*axpy_gram)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
+                   const Ctrl* ctrl, int sms, int* launches);
+  int (*rescale_add)(cudaStream_t st, cd* dst, const cd* L, const cd* src, double r, long long V, int sms,
+                     int* launches);
+  int (*trsm)(cudaStream_t st, cd* Q, const cd* R, long long V, const Ctrl* ctrl, int sms, int* launches);
+  int (*shift_update)(cudaStream_t st, cd* Q, const ShiftPtrs* fp, const cd* R, const cd* A, const cd* B,
+                      long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl, int sms,
+                      int* launches);
+  int (*max_partials)(int sms);
+  void (*prepare)(int sms);  // occupancy queries / smem opt-in; call once outside stream capture
+};
+
+const OpsTable* get_ops(int N);  // nullptr if N is not compiled in
+
+#ifdef BCG_N  // ---- per-N implementation, included only by inst.cu ----------------------------
+
+constexpr int kNT = 192;  // 6 warps: one 4x4 Gram block per warp at N = 12, whole sites per CTA
+
+template <int N>
+struct Tune {
+  // rhs columns per stencil work item (must divide N)
+  static constexpr int R = (N % 3 == 0) ? 3 : (N % 2 == 0) ? 2 : 1;
+};
+
+template <typename K>
+static int occupancy_blocks(K kernel, int threads, size_t smem, int sms) {
+  int nb = 0;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
+  return (nb < 1 ? 1 : nb) * sms;
+}
+
+template <int N>
+struct Ops {
+  static constexpr int R = Tune<N>::R;
+  using DG = DiracGeom<N, R, kNT>;
+  using AG = AxpyGeom<N, kNT>;
+  using GG = GramKGeom<N, kNT>;
+  static constexpr bool FUSED = DG::CAN_GRAM && AG::CAN_GRAM;
+  static constexpr int GRAM_Y = (GramGeom<N>::NTASK + (kNT / 32) - 1) / (kNT / 32);
+  static constexpr size_t SHIFT_SMEM = sizeof(cd) * 5 * N * N;
+
+  // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
+  // outside any stream capture -- and used to size the persistent grids.
+  struct Caps {
+    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0;
+  };
+  static Caps& caps() {
+    static Caps c;
+    return c;
+  }
+  static void prepare(int sms) {
+    Caps& c = caps();
+    if (c.dirac) return;
+    if constexpr (FUSED) {
+      c.dirac_g = occupancy_blocks(dirac_kernel<N, R, kNT, true>, kNT, DG::SMEM_BYTES, sms);
+      c.axpy_g = occupancy_blocks(axpy_gram_kernel<N, kNT, true>, kNT, AG::SMEM_BYTES, sms);
+    }
+    c.dirac = occupancy_blocks(dirac_kernel<N, R, kNT, false>, kNT, DG::SMEM_BYTES, sms);
+    c.gram = occupancy_blocks(gram_kernel<N, kNT>, kNT, GG::SMEM_BYTES, sms);
+    c.axpy = occupancy_blocks(axpy_gram_kernel<N, kNT, false>, kNT, sizeof(cd) * N * N, sms);
+    c.rescale = occupancy_blocks(rescale_add_kernel<N, kNT>, kNT, 0, sms);
+    c.trsm = occupancy_blocks(trsm_kernel<N, kNT>, kNT, 0, sms);
+    c.shift = occupancy_blocks(shift_update_kernel<N, kNT>, kNT, SHIFT_SMEM, sms);
+  }
+
+  static int err() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -static_cast<int>(e);
+  }
+  static int clamp_grid(long long ntiles, int cap) {
+    int grid = static_cast<int>(ntiles < cap ? ntiles : cap);
+    return grid < 1 ? 1 : grid;
+  }
+
+  static int gram(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
+                  int* launches) {
+    prepare(sms);
+    const int grid = clamp_grid((V + GG::TS - 1) / GG::TS, caps().gram);
+    gram_kernel<N, kNT><<<dim3(grid, GRAM_Y), kNT, GG::SMEM_BYTES, st>>>(A, B, V, gpart, ctrl);
+    if (launches) ++*launches;
+    int e = err();
+    return e ? e : grid;
+  }
+
+  static int dirac(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
+                   cd* gpart, const Ctrl* ctrl, int sms, int* launches) {
+    prepare(sms);
+    const long long ntiles = (V + DG::TS - 1) / DG::TS;
+    if (gpart != nullptr) {
+      if constexpr (FUSED) {
+        const int grid = clamp_grid(ntiles, caps().dirac_g);
+        dirac_kernel<N, R, kNT, true><<<grid, kNT, DG::SMEM_BYTES, st>>>(in, out, U, V, m2, sigma, gpart, ctrl);
+        if (launches) ++*launches;
+        int e = err();
+        return e ? e : grid;
+      }
+    }
+    const int grid = clamp_grid(ntiles, caps().dirac);
+    dirac_kernel<N, R, kNT, false><<<grid, kNT, DG::SMEM_BYTES, st>>>(in, out, U, V, m2, sigma, nullptr, ctrl);
+    if (launches) ++*launches;
+    int e = err();
+    if (e) return e;
+    if (gpart != nullptr) return gram(st, in, out, V, gpart, ctrl, sms, launches);
+    return 0;
+  }
+
+  static int axpy_gram(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
+                       const Ctrl* ctrl, int sms, int* launches) {
+    prepare(sms);
+    const long long ntiles = (3 * V + kNT - 1) / kNT;
+    if (gpart != nullptr) {
+      if constexpr (FUSED) {
+        const int grid = clamp_grid(ntiles, caps().axpy_g);
+        axpy_gram_kernel<N, kNT, true><<<grid, kNT, AG::SMEM_BYTES, st>>>(Q, T, M, V, gpart, ctrl);
+        if (launches) ++*launches;
+        int e = err();
+        return e ? e : grid;
+      }
+    }
+    const int grid = clamp_grid(ntiles, caps().axpy);
+    axpy_gram_kernel<N, kNT, false><<<grid, kNT, sizeof(cd) * N * N, st>>>(Q, T, M, V, nullptr, ctrl);
+    if (launches) ++*launches;
+    int e = err();
+    if (e) return e;
+    if (gpart != nullptr) return gram(st, Q, Q, V, gpart, ctrl, sms, launches);
+    return 0;
+  }
+
+  static int rescale_add(cudaStream_t st, cd* dst, const cd* L, const cd* src, double r, long long V, int sms,
+                         int* launches) {
+    prepare(sms);
+    rescale_add_kernel<N, kNT><<<clamp_grid((3 * V + kNT - 1) / kNT, caps().rescale), kNT, 0, st>>>(dst, L, src, r, V);
+    if (launches) ++*launches;
+    return err();
+  }
+
+  static int trsm(cudaStream_t st, cd* Q, const cd* Rm, long long V, const Ctrl* ctrl, int sms, int* launches) {
+    prepare(sms);
+    trsm_kernel<N, kNT><<<clamp_grid((3 * V + kNT - 1) / kNT, caps().trsm), kNT, 0, st>>>(Q, Rm, V, ctrl);
+    if (launches) ++*launches;
+    return err();
+  }
+
+  static int shift_update(cudaStream_t st, cd* Q, const ShiftPtrs* fp, const cd* Rm, const cd* A, const cd* B,
+                          long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl, int sms,
+                          int* launches) {
+    prepare(sms);
+    shift_update_kernel<N, kNT><<<clamp_grid((3 * V + kNT - 1) / kNT, caps().shift), kNT, SHIFT_SMEM, st>>>(
+        Q, *fp, Rm, A, B, V, do_backsub, n_active_fixed, ctrl);
+    if (launches) ++*launches;
+    return err();
+  }
+
+  static int max_partials(int sms) { return 32 * sms; }
+};
+
+template <int N>
+const OpsTable* make_ops() {
+  static const OpsTable t = {N,
+                             Tune<N>::R,
+                             DiracGeom<N, Tune<N>::R, kNT>::TS,
+                             Ops<N>::FUSED ? 1 : 0,
+                             &Ops<N>::dirac,
+                             &Ops<N>::gram,
+                             &Ops<N>::axpy_gram,
+                             &Ops<N>::rescale_add,
+                             &Ops<N>::trsm,
+                             &Ops<N>::shift_update,
+                             &Ops<N>::max_partials,
+                             &Ops<N>::prepare};
+  return &t;
+}
+#endif  // BCG_N
+
+}  // namespace bcg

@@ -1,0 +1,148 @@
+/* blockcg_b200 -- C-ABI of the B200-native block-CG hot path.
+ *
+ * This is the ONLY surface through which host code reaches the CUDA kernels:
+ * plain pointers, sizes and opaque handles, no C++/torch types.  It replaces,
+ * for the hot path only, what the reference does inside its header templates
+ * (citations relative to the lkeegan/blockCG tree):
+ *
+ *   bcg_solve_bcg     <- BCG<N>      inc/block_solvers.hpp:10-45
+ *   bcg_solve_bcgrq   <- BCGrQ<N>    inc/block_solvers.hpp:50-86
+ *   bcg_solve_sbcgrq  <- SBCGrQ<N>   inc/block_solvers.hpp:91-185
+ *   bcg_op            <- dirac_op::op<N>                 inc/dirac_op.hpp:36-43
+ *   bcg_set_links     <- dirac_op ctor / private U       inc/dirac_op.hpp:9-11,24-32
+ *   bcg_gram          <- block_fermion_field::hermitian_dot   inc/fields.hpp:103-122
+ *   bcg_add           <- block_fermion_field::add             inc/fields.hpp:70-77
+ *   bcg_rescale_add   <- block_fermion_field::rescale_add     inc/fields.hpp:79-90
+ *   bcg_trsm          <- multiply_upper_triangular_inverse_RHS inc/fields.hpp:125-136
+ *   bcg_thinqr        <- block_fermion_field::thinQR          inc/fields.hpp:140-146
+ *
+ * Memory layouts are the reference's own, as interleaved (re,im) doubles:
+ *   field  : [V][N][3] complex128 (site-major, 3xN column-major per site)
+ *   links  : [V][3][3] complex128 (column-major 3x3 per site)
+ *   matrix : N x N complex128, column-major
+ *
+ * Every function returns 0 on success or a bcg_status code; no exception ever
+ * crosses this boundary.  bcg_last_error() gives a human-readable message.
+ * A context is bound to one CUDA device and one host thread at a time.
+ * There is no CPU fallback: without a CUDA device bcg_ctx_create fails.
+ */
+#ifndef BLOCKCG_B200_H
+#define BLOCKCG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bcg_ctx bcg_ctx;
+
+typedef enum {
+  BCG_OK = 0,
+  BCG_ERR_INVALID = 1,       /* bad argument (null pointer, unsupported N, ...) */
+  BCG_ERR_CUDA = 2,          /* a CUDA runtime call failed                       */
+  BCG_ERR_NOT_PD = 3,        /* Gram matrix not positive definite (LLT pivot <= 0;
+                                the reference leaves this unchecked, LLT.h:449)  */
+  BCG_ERR_NCCL = 4,          /* a NCCL call failed                               */
+  BCG_ERR_NO_COMM = 5,       /* multi-rank context used before bcg_comm_init     */
+  BCG_ERR_NAN = 6            /* residual became NaN (the reference exits its loop
+                                silently in that case)                           */
+} bcg_status;
+
+#define BCG_MAX_SHIFTS 32
+#define BCG_UNIQUE_ID_BYTES 128
+
+/* ---- library / build info -------------------------------------------------------- */
+const char* bcg_version(void);
+/* 1 if kernels for this N_rhs are compiled in (the reference fixes N at compile
+ * time, inc/fields.hpp:19-25; here it is a run-time argument). */
+int bcg_supports_nrhs(int n_rhs);
+
+/* ---- context ---------------------------------------------------------------------- */
+/* v_local   : number of sites owned by this rank (contiguous slab of the global
+ *             site index; for one rank = the reference's V).
+ * n_rhs     : N_rhs.     max_shifts : largest shift count SBCGrQ will be asked for.
+ * device    : CUDA device ordinal.
+ * rank/nranks : position in the slab decomposition (0/1 for a single GPU). */
+int bcg_ctx_create(bcg_ctx** ctx, int64_t v_local, int n_rhs, int max_shifts, int device, int rank,
+                   int nranks);
+int bcg_ctx_destroy(bcg_ctx* ctx);
+const char* bcg_last_error(const bcg_ctx* ctx);
+
+/* multi-GPU plumbing: rank 0 obtains an id, the host distributes it (e.g. with
+ * torch.distributed / MPI), every rank calls bcg_comm_init. */
+int bcg_comm_get_unique_id(void* id_out /* BCG_UNIQUE_ID_BYTES */);
+int bcg_comm_init(bcg_ctx* ctx, const void* id /* BCG_UNIQUE_ID_BYTES */);
+
+/* ---- operator --------------------------------------------------------------------- */
+/* links_host: this rank's [v_local][3][3] links; halos (2 sites each side) are
+ * filled by periodic wrap (1 rank) or neighbour exchange (nranks > 1). */
+int bcg_set_links(bcg_ctx* ctx, const double* links_host, double mass);
+
+/* ---- device-resident fields --------------------------------------------------------- */
+int bcg_field_alloc(bcg_ctx* ctx, int* handle_out);
+int bcg_field_free(bcg_ctx* ctx, int handle);
+int bcg_field_upload(bcg_ctx* ctx, int handle, const double* host);   /* [v_local][N][3] */
+int bcg_field_download(bcg_ctx* ctx, int handle, double* host);
+int bcg_field_zero(bcg_ctx* ctx, int handle);
+int bcg_field_copy(bcg_ctx* ctx, int dst, int src);
+
+/* ---- primitives (unit tests, micro-benchmarks, verification) -------------------------- */
+/* out = (m^2 - D^2) in + sigma * in      (sigma = 0 for the bare operator)
+ * gram_host (optional, may be NULL): receives in^dag out, the Gram fused into
+ * the stencil epilogue. */
+int bcg_op(bcg_ctx* ctx, int out, int in, double sigma, double* gram_host);
+/* R = a^dag b: lower triangle + diagonal accumulated, upper = conj mirror. */
+int bcg_gram(bcg_ctx* ctx, int a, int b, double* r_host);
+/* dst += src * M   (M: N x N, host) */
+int bcg_add(bcg_ctx* ctx, int dst, int src, const double* m_host);
+/* dst += src * s   (real scalar; block_solvers.hpp:136) */
+int bcg_add_scalar(bcg_ctx* ctx, int dst, int src, double s);
+/* dst = dst * L + src * r */
+int bcg_rescale_add(bcg_ctx* ctx, int dst, const double* l_host, int src, double r);
+/* q <- q R^-1, R upper triangular (back substitution, column order of the reference) */
+int bcg_trsm(bcg_ctx* ctx, int q, const double* r_host);
+/* CholQR: R = chol(q^dag q)^dag, q <- q R^-1; r_host receives R (zero below diag). */
+int bcg_thinqr(bcg_ctx* ctx, int q, double* r_host);
+/* sqrt(diag((A+sigma)x - b)^dag(...) / diag(b^dag b)) per rhs: the reference's only
+ * acceptance criterion (benchmark.cpp:93-103, test/solvers.cpp:99-118). */
+int bcg_true_residual(bcg_ctx* ctx, int x, int b, double sigma, double* res_host /* [N] */);
+
+/* ---- solvers on device-resident fields (benchmark path: no PCIe traffic in the loop) --- */
+typedef struct {
+  int iterations;          /* number of operator applications (the reference's return value) */
+  double residual;         /* solver's own residual estimate at exit                       */
+  int n_unconverged;       /* SBCGrQ: shifts still being updated at exit                    */
+  double solve_ms;         /* device time of the iteration loop (CUDA events)               */
+  double setup_ms;         /* device time of the setup (thinQR of B, copies)                */
+  int64_t kernel_launches; /* kernels launched by this solve                                */
+} bcg_solve_info;
+
+int bcg_solve_bcg_dev(bcg_ctx* ctx, int x, int b, double eps, int max_iterations, bcg_solve_info* info);
+int bcg_solve_bcgrq_dev(bcg_ctx* ctx, int x, int b, double eps, int max_iterations, bcg_solve_info* info);
+/* x_handles[n_shifts]; sigma ascending, sigma[0] >= 0 (block_solvers.hpp:97-101) */
+int bcg_solve_sbcgrq_dev(bcg_ctx* ctx, const int* x_handles, int b, const double* sigma, int n_shifts,
+                         double eps, double eps_shifts, int max_iterations, bcg_solve_info* info);
+
+/* ---- solvers on host buffers (drop-in for the reference's templates) -------------------- */
+int bcg_solve_bcg(bcg_ctx* ctx, double* x_host, const double* b_host, double eps, int max_iterations,
+                  bcg_solve_info* info);
+int bcg_solve_bcgrq(bcg_ctx* ctx, double* x_host, const double* b_host, double eps, int max_iterations,
+                    bcg_solve_info* info);
+/* x_host: n_shifts pointers, each to a [v_local][N][3] buffer */
+int bcg_solve_sbcgrq(bcg_ctx* ctx, double* const* x_host, const double* b_host, const double* sigma,
+                     int n_shifts, double eps, double eps_shifts, int max_iterations, bcg_solve_info* info);
+
+/* ---- micro-benchmark hooks (timed on the context's stream with CUDA events) -------------- */
+/* Runs `reps` back-to-back launches of one kernel and returns the mean device
+ * time per launch in *ms_out.  which: 0 dirac apply (+fused Gram), 1 dirac apply only,
+ * 2 Gram, 3 Q -= T*alpha with fused Gram, 4 multishift update over n_shifts shifts,
+ * 5 X += P*M, 6 P = P*L + Q.  Fields are the context's own scratch, filled by the caller
+ * through handles f0..f3 where needed. */
+int bcg_bench_kernel(bcg_ctx* ctx, int which, int reps, int n_shifts, const int* handles, int n_handles,
+                     double* ms_out, int64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOCKCG_B200_H */

@@ -1,0 +1,56 @@
+"""Kernel micro-benchmarks through the C-ABI (bcg_bench_kernel): mean device time per
+launch with CUDA events on the library's stream, inputs larger than L2 where the
+volume allows, algorithmic GB/s per SURVEY 8(d).
+
+    python tools/microbench.py [--V 331776] [--N 12] [--S 9] [--reps 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import blockcg_b200  # noqa: E402
+
+
+def run(V, N, S, reps, seed=0):
+    rng = np.random.default_rng(seed)
+    U = rng.uniform(-1, 1, (V, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 3, 3))
+    out = {"V": V, "N": N, "S": S, "reps": reps}
+    F = 48.0 * N * V
+    Ub = 144.0 * V
+    with blockcg_b200.Context(V, N, max_shifts=S) as ctx:
+        ctx.set_links(U, 1e-3)
+        data = rng.uniform(-1, 1, (V, N, 3)) + 1j * rng.uniform(-1, 1, (V, N, 3))
+        hs = [ctx.field(data) for _ in range(2)]
+        hs += [ctx.field() for _ in range(2 * S - 1)]
+        for h in hs[2:]:
+            ctx.copy(h, hs[0])
+        kernels = [
+            ("dirac_gram", 0, hs[:2], 1, 2 * F + Ub),
+            ("dirac", 1, hs[:2], 1, 2 * F + Ub),
+            ("gram", 2, hs[:2], 1, 2 * F),
+            ("axpy_gram", 3, hs[:2], 1, 3 * F),
+            ("axpy", 5, hs[:2], 1, 3 * F),
+            ("rescale_add", 6, hs[:2], 1, 3 * F),
+            ("shift_update_S%d" % S, 4, hs[:1 + 2 * S], S, (2 + 4 * S) * F),
+            ("shift_update_S1", 4, hs[:3], 1, 6 * F),
+        ]
+        for name, which, handles, ns, bytes_alg in kernels:
+            ms, nl = ctx.bench_kernel(which, reps, handles, ns)
+            out[name] = {"ms": ms, "alg_GBps": bytes_alg / ms / 1e6, "launches": nl}
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--V", type=int, nargs="+", default=[331776])
+    ap.add_argument("--N", type=int, nargs="+", default=[12])
+    ap.add_argument("--S", type=int, default=9)
+    ap.add_argument("--reps", type=int, default=20)
+    a = ap.parse_args()
+    for V in a.V:
+        for N in a.N:
+            print(json.dumps(run(V, N, a.S, a.reps)), flush=True)
