@@ -370,10 +370,11 @@ __device__ __forceinline__ void row_store(cd* __restrict__ f, long long row_base
 }
 template <int N>
 __device__ __forceinline__ void row_mm_acc(cd (&out)[N], const cd (&p)[N], const cd* __restrict__ sM) {
+  // k outer / j inner: N independent accumulator chains between dependent DFMAs
 #pragma unroll
-  for (int j = 0; j < N; ++j)
+  for (int k = 0; k < N; ++k)
 #pragma unroll
-    for (int k = 0; k < N; ++k) cmac(out[j], p[k], lds_cd(sM + k + N * j));
+    for (int j = 0; j < N; ++j) cmac(out[j], p[k], lds_cd(sM + k + N * j));
 }
 __device__ __forceinline__ long long row_base_of(long long row, int N) {
   const long long site = row / 3;
@@ -482,13 +483,24 @@ static __global__ void sub_kernel(cd* dst, const cd* a, const cd* __restrict__ b
 
 // In-register back substitution of one row: q <- q R^-1 in the reference's
 // column order (fields.hpp:125-136); R upper triangular, column-major in smem.
+// The diagonal of sR must already hold the RECIPROCALS 1/R(i,i) (see load_tri_recip):
+// one complex multiply per column instead of a double-precision division per row.
 template <int N>
 __device__ __forceinline__ void row_backsub(cd (&q)[N], const cd* __restrict__ sR) {
 #pragma unroll
   for (int i = 0; i < N; ++i) {
 #pragma unroll
     for (int j = 0; j < i; ++j) cmsub(q[i], lds_cd(sR + j + N * i), q[j]);
-    q[i] = cdiv(q[i], lds_cd(sR + i + N * i));
+    q[i] = cmul(q[i], lds_cd(sR + i + N * i));
+  }
+}
+// stage an upper-triangular R into shared memory with its diagonal inverted
+template <int N>
+__device__ __forceinline__ void load_tri_recip(cd* sR, const cd* __restrict__ Rm) {
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    cd v = Rm[e];
+    if (e % N == e / N) v = cdiv(cmake(1.0, 0.0), v);
+    sR[e] = v;
   }
 }
 
@@ -498,7 +510,7 @@ trsm_kernel(cd* __restrict__ Q, const cd* __restrict__ Rm, long long V, const Ct
   if (ctrl != nullptr && ctrl->done) return;
   __shared__ cd sR[N * N];
   const int tid = threadIdx.x;
-  for (int e = tid; e < N * N; e += NT) sR[e] = Rm[e];
+  load_tri_recip<N>(sR, Rm);
   __syncthreads();
   const long long nrows = 3 * V;
   for (long long row = static_cast<long long>(blockIdx.x) * NT + tid; row < nrows;
@@ -527,19 +539,16 @@ struct ShiftPtrs {
 };
 
 template <int N, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, (N <= 12) ? 2 : 1)
 shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
                     const cd* __restrict__ Amats, const cd* __restrict__ Bmats, long long V,
                     int do_backsub, int n_active_fixed, const Ctrl* __restrict__ ctrl) {
   if (ctrl != nullptr && ctrl->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* sR = reinterpret_cast<cd*>(smem_raw);
-  cd* sA[2] = {sR + N * N, sR + 2 * N * N};
-  cd* sB[2] = {sR + 3 * N * N, sR + 4 * N * N};
   const int tid = threadIdx.x;
   const int n_active = (n_active_fixed > 0) ? n_active_fixed : ctrl->n_unconv;
-  if (do_backsub)
-    for (int e = tid; e < N * N; e += NT) sR[e] = Rm[e];
+  if (do_backsub) load_tri_recip<N>(sR, Rm);
   const long long nrows = 3 * V;
   const long long ntiles = (nrows + NT - 1) / NT;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -548,10 +557,11 @@ shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
     const long long rb = live ? row_base_of(row, N) : 0;
     cd q[N];
     for (int s = 0; s < n_active; ++s) {
-      const int buf = s & 1;
+      cd* sAb = sR + (1 + (s & 1)) * N * N;  // double-buffered coefficient pair
+      cd* sBb = sR + (3 + (s & 1)) * N * N;
       for (int e = tid; e < N * N; e += NT) {
-        sA[buf][e] = Amats[static_cast<size_t>(s) * N * N + e];
-        sB[buf][e] = Bmats[static_cast<size_t>(s) * N * N + e];
+        sAb[e] = Amats[static_cast<size_t>(s) * N * N + e];
+        sBb[e] = Bmats[static_cast<size_t>(s) * N * N + e];
       }
       __syncthreads();
       if (live) {
@@ -567,14 +577,14 @@ shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
         {
           cd x[N];
           row_load<N>(fp.X[s], rb, x);
-          row_mm_acc<N>(x, p, sA[buf]);
+          row_mm_acc<N>(x, p, sAb);
           row_store<N>(fp.X[s], rb, x);
         }
         {
           cd pn[N];
 #pragma unroll
           for (int j = 0; j < N; ++j) pn[j] = czero();
-          row_mm_acc<N>(pn, p, sB[buf]);
+          row_mm_acc<N>(pn, p, sBb);
 #pragma unroll
           for (int j = 0; j < N; ++j) pn[j] = cadd(pn[j], q[j]);  // tmp = P*L ; tmp += Q*1.0 (fields.hpp:85-86)
           row_store<N>(fp.P[s], rb, pn);
