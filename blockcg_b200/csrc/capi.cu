@@ -858,7 +858,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   const double m2 = c->mass * c->mass;
   ShiftPtrs fp;
   std::memset(&fp, 0, sizeof fp);
-  if (which == 4) {
+  if (which == 4 || which == 7 || which == 8) {
     if (nh < 1 + 2 * n_shifts || n_shifts < 1 || n_shifts > c->S) return fail(c, BCG_ERR_INVALID, "need 1+2S handles");
     for (int s = 0; s < n_shifts; ++s) {
       fp.X[s] = fptr(c, h[1 + 2 * s]);
@@ -886,6 +886,14 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         KL(c->ops->shift_update(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
                                 c->mats + c->L.B(0), c->V, 1, n_shifts, nullptr, c->sms, l));
         break;
+      case 8:  // diagnostic: the pipelined kernel's TMA load/store ring with the arithmetic skipped
+        KL(c->ops->shift_update(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
+                                c->mats + c->L.B(0), c->V, 3, n_shifts, nullptr, c->sms, l));
+        break;
+      case 7:
+        KL(c->ops->shift_update_direct(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
+                                       c->mats + c->L.B(0), c->V, 1, n_shifts, nullptr, c->sms, l));
+        break;
       case 5:
         KL(c->ops->axpy_gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, nullptr, nullptr,
                              c->sms, l));
@@ -905,7 +913,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
     std::vector<cd> I(nn, make_double2(0, 0)), Z(nn, make_double2(0, 0));
     for (int i = 0; i < c->N; ++i) I[i + c->N * i] = make_double2(1.0, 0.0);
     for (size_t e = 0; e < nn; ++e) Z[e] = make_double2(1e-3 * ((e * 7) % 5), -1e-3 * ((e * 3) % 7));
-    CU(cudaMemcpy(mat(c, M_SCRATCH), which == 4 ? I.data() : Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(mat(c, M_SCRATCH), (which == 4 || which == 7 || which == 8) ? I.data() : Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
     for (int s = 0; s < c->S; ++s) {
       CU(cudaMemcpy(c->mats + c->L.A(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(c->mats + c->L.B(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));

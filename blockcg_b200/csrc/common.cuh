@@ -50,6 +50,19 @@ __device__ __forceinline__ cd cdiv(cd a, cd b) {
   return make_double2((a.x * br + a.y * bi) / d, (a.y * br - a.x * bi) / d);
 }
 
+// Coefficient operands of the multishift update are stored "interleaved by column
+// group": the pipelined kernel gives every site to NSPLIT lanes, lane h producing the
+// JC = N/NSPLIT output columns h*JC .. h*JC+JC-1, and the NSPLIT lanes read adjacent
+// 16-byte words: element (k, j) of the N x N matrix sits at
+// ((k*JC + j%JC)*NSPLIT + j/JC).
+__host__ __device__ constexpr int shift_nsplit(int N) {
+  return (N % 4 == 0 && N >= 8) ? 4 : (N % 2 == 0 && N >= 4) ? 2 : 1;
+}
+__host__ __device__ inline int shift_mat_index(int N, int k, int j) {
+  const int ns = shift_nsplit(N), jc = N / ns;
+  return (k * jc + (j % jc)) * ns + j / jc;
+}
+
 // ---- loop control block living in device memory -------------------------------------
 // The iteration loop never round-trips to the host: every kernel of an
 // iteration looks at `done` (and the stencil at `stop`) and returns early, so
@@ -84,6 +97,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(

@@ -368,6 +368,15 @@ __device__ __forceinline__ void row_store(cd* __restrict__ f, long long row_base
 #pragma unroll
   for (int k = 0; k < N; ++k) f[row_base + 3 * k] = r[k];
 }
+// same product with the operand in the interleaved layout of shift_mat_index()
+template <int N>
+__device__ __forceinline__ void row_mm_acc_il(cd (&out)[N], const cd (&p)[N], const cd* __restrict__ sM) {
+  constexpr int NS = shift_nsplit(N), JC = N / NS;
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+#pragma unroll
+    for (int j = 0; j < N; ++j) cmac(out[j], p[k], lds_cd(sM + (k * JC + (j % JC)) * NS + j / JC));
+}
 template <int N>
 __device__ __forceinline__ void row_mm_acc(cd (&out)[N], const cd (&p)[N], const cd* __restrict__ sM) {
   // k outer / j inner: N independent accumulator chains between dependent DFMAs
@@ -548,7 +557,8 @@ shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
   cd* sR = reinterpret_cast<cd*>(smem_raw);
   const int tid = threadIdx.x;
   const int n_active = (n_active_fixed > 0) ? n_active_fixed : ctrl->n_unconv;
-  if (do_backsub) load_tri_recip<N>(sR, Rm);
+  if (do_backsub)
+    for (int e = tid; e < N * N; e += NT) sR[e] = Rm[e];  // diagonal already inverted (M_RHO_RECIP)
   const long long nrows = 3 * V;
   const long long ntiles = (nrows + NT - 1) / NT;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -577,14 +587,14 @@ shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
         {
           cd x[N];
           row_load<N>(fp.X[s], rb, x);
-          row_mm_acc<N>(x, p, sAb);
+          row_mm_acc_il<N>(x, p, sAb);
           row_store<N>(fp.X[s], rb, x);
         }
         {
           cd pn[N];
 #pragma unroll
           for (int j = 0; j < N; ++j) pn[j] = czero();
-          row_mm_acc<N>(pn, p, sBb);
+          row_mm_acc_il<N>(pn, p, sBb);
 #pragma unroll
           for (int j = 0; j < N; ++j) pn[j] = cadd(pn[j], q[j]);  // tmp = P*L ; tmp += Q*1.0 (fields.hpp:85-86)
           row_store<N>(fp.P[s], rb, pn);
@@ -592,6 +602,249 @@ shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
       }
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K4 (pipelined): the same multishift update as a warp-specialised bulk-TMA pipeline.
+//
+//   1 producer warp : per-site cp.async.bulk loads of {P_s tile, X_s tile} plus the
+//                     coefficient pair {A_s, B_s} (and {Q tile, R'} once per tile) into a
+//                     2-stage shared-memory ring, and the bulk stores of the updated
+//                     tiles back to HBM.  Sites land with a padded pitch so that the
+//                     compute warps' row accesses are bank-conflict free.
+//   NCW compute warps: a site (3 colour rows) is owned by NSPLIT lanes of one warp, lane h
+//                     producing JC = N/NSPLIT output columns for all three rows, so every
+//                     coefficient word fetched from shared memory feeds 3 complex MACs
+//                     (12 DFMA) and every P word feeds JC of them.  Rows are updated in
+//                     place in the stage buffer.
+// Stage hand-off is by mbarriers only (full[]: TMA -> compute, computed[]: compute ->
+// producer).  The one intra-warp hazard (a lane overwriting P columns its partner lanes
+// still read) is closed by a __syncwarp() between the last read and the first write.
+// Coefficients arrive in the interleaved layout of shift_mat_index(); Rrecip is rho with
+// its diagonal already inverted.  Bit 1 of do_backsub skips the arithmetic (diagnostic:
+// measures the bare load/store ring).
+// ------------------------------------------------------------------------------------
+template <int N, int TS>
+struct ShiftGeom {
+  static constexpr int NSPLIT = shift_nsplit(N);
+  static constexpr int JC = N / NSPLIT;
+  static constexpr int SPW = 32 / NSPLIT;  // sites per compute warp
+  static_assert(TS % SPW == 0, "tile must fill whole warps");
+  static constexpr int NCW = TS / SPW;     // compute warps
+  static constexpr int NT = (NCW + 1) * 32;
+  static constexpr int SITE = 3 * N;       // complex per site in HBM
+  // Sites are staged in PAIRS (one bulk copy of 2 sites) with one 16-byte word of padding
+  // per pair when the pair would otherwise start on the same banks as its neighbour:
+  // the 8 sites a warp touches per instruction then start on 8 distinct 4-bank groups.
+  static_assert(TS % 2 == 0, "tile holds whole site pairs");
+  static constexpr int PAIR = 2 * SITE + (((2 * SITE) % 2 == 0) ? 1 : 0);
+  static constexpr int TILE = (TS / 2) * PAIR;  // complex per staged field tile
+  static constexpr int STAGE_ELEMS = 2 * TILE + 2 * N * N;
+  static constexpr int NSTAGE = 2;
+  static constexpr size_t SMEM_BYTES = sizeof(cd) * NSTAGE * STAGE_ELEMS + 64;
+  static constexpr int MAXREG = (2 * SMEM_BYTES <= 220 * 1024) ? 128 : 232;
+};
+
+template <int N, int TS>
+__global__ void __maxnreg__((ShiftGeom<N, TS>::MAXREG))
+shift_pipe_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rrecip,
+                  const cd* __restrict__ Amats, const cd* __restrict__ Bmats, long long V, int do_backsub,
+                  int n_active_fixed, const Ctrl* __restrict__ ctrl) {
+  using Geo = ShiftGeom<N, TS>;
+  constexpr int NSPLIT = Geo::NSPLIT, JC = Geo::JC, SPW = Geo::SPW, NCW = Geo::NCW, SITE = Geo::SITE;
+  constexpr int PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE_ELEMS;
+  if (ctrl != nullptr && ctrl->done) return;
+  const int n_active = (n_active_fixed > 0) ? n_active_fixed : ctrl->n_unconv;
+  const bool backsub = (do_backsub & 1) != 0, arith = (do_backsub & 2) == 0;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cd* sbuf = reinterpret_cast<cd*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sbuf + Geo::NSTAGE * STAGE);
+  uint64_t* computed = full + Geo::NSTAGE;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < Geo::NSTAGE; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(computed + s, NCW * 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long long ntiles = (V + TS - 1) / TS;
+  constexpr uint32_t MAT_BYTES = N * N * sizeof(cd);
+  constexpr uint32_t SITE_BYTES = SITE * sizeof(cd);
+
+  if (warp == NCW) {
+    // ===================== producer warp: lane l moves sites l, l+32, ... =====================
+    long long it = 0;
+    long long rx0_a = 0, rx0_b = 0;  // descriptors of the two items in flight
+    int rns_a = 0, rns_b = 0, rs_a = 0, rs_b = 0;
+    auto store_item = [&](int st) {
+      const cd* buf = sbuf + st * STAGE;
+      const int ns = st ? rns_b : rns_a;
+      const long long x0 = st ? rx0_b : rx0_a;
+      const int s = st ? rs_b : rs_a;
+      for (int lp = lane; 2 * lp < ns; lp += 32) {  // lane lp moves site pair lp (last one may be single)
+        const long long off = (x0 + 2 * lp) * SITE;
+        const uint32_t bytes = (2 * lp + 1 < ns) ? 2 * SITE_BYTES : SITE_BYTES;
+        if (s < 0) {
+          if (backsub) bulk_s2g(Q + off, buf + lp * PAIR, bytes);
+        } else {
+          bulk_s2g(fp.P[s] + off, buf + lp * PAIR, bytes);
+          bulk_s2g(fp.X[s] + off, buf + TILE + lp * PAIR, bytes);
+        }
+      }
+      bulk_commit();
+    };
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long x0 = tile * TS;
+      const int ns = static_cast<int>(min(static_cast<long long>(TS), V - x0));
+      for (int s = -1; s < n_active; ++s, ++it) {
+        const int st = static_cast<int>(it & 1);
+        const uint32_t use = static_cast<uint32_t>(it >> 1);
+        if (it >= 2) {
+          mbar_wait(computed + st, (use - 1) & 1u);  // item it-2 has been computed in place
+          store_item(st);
+          bulk_wait_read0();  // this lane's stores have drained the buffer
+          __syncwarp();
+        }
+        if (st) {
+          rx0_b = x0; rns_b = ns; rs_b = s;
+        } else {
+          rx0_a = x0; rns_a = ns; rs_a = s;
+        }
+        cd* buf = sbuf + st * STAGE;
+        if (lane == 0) {
+          const uint32_t fld = static_cast<uint32_t>(ns) * SITE_BYTES;
+          if (s < 0) {
+            mbar_arrive_expect_tx(full + st, fld + (backsub ? MAT_BYTES : 0u));
+            if (backsub) bulk_g2s(buf + 2 * TILE, Rrecip, MAT_BYTES, full + st);
+          } else {
+            mbar_arrive_expect_tx(full + st, 2 * fld + 2 * MAT_BYTES);
+            bulk_g2s(buf + 2 * TILE, Amats + static_cast<size_t>(s) * N * N, MAT_BYTES, full + st);
+            bulk_g2s(buf + 2 * TILE + N * N, Bmats + static_cast<size_t>(s) * N * N, MAT_BYTES, full + st);
+          }
+        }
+        __syncwarp();  // expect_tx is registered before any lane's copy can complete
+        for (int lp = lane; 2 * lp < ns; lp += 32) {
+          const long long off = (x0 + 2 * lp) * SITE;
+          const uint32_t bytes = (2 * lp + 1 < ns) ? 2 * SITE_BYTES : SITE_BYTES;
+          if (s < 0) {
+            bulk_g2s(buf + lp * PAIR, Q + off, bytes, full + st);
+          } else {
+            bulk_g2s(buf + lp * PAIR, fp.P[s] + off, bytes, full + st);
+            bulk_g2s(buf + TILE + lp * PAIR, fp.X[s] + off, bytes, full + st);
+          }
+        }
+      }
+    }
+    // drain the last (up to two) items
+    for (long long k = (it >= 2 ? it - 2 : 0); k < it; ++k) {
+      const int st = static_cast<int>(k & 1);
+      mbar_wait(computed + st, static_cast<uint32_t>(k >> 1) & 1u);
+      store_item(st);
+    }
+    bulk_wait0();
+    return;
+  }
+
+  // ===================== compute warps =====================
+  const int h = lane % NSPLIT;                 // column group of this lane
+  const int lsite = warp * SPW + lane / NSPLIT;  // site within the tile
+  const int sbase = (lsite >> 1) * PAIR + (lsite & 1) * SITE;
+  long long it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long x0 = tile * TS;
+    const int ns = static_cast<int>(min(static_cast<long long>(TS), V - x0));
+    const bool live = lsite < ns;
+    cd qh[3][JC];
+    {  // ---- Q item: lanes h = 0,1,2 back-substitute colour row h, then everybody picks its columns ----
+      const int st = static_cast<int>(it & 1);
+      mbar_wait(full + st, static_cast<uint32_t>(it >> 1) & 1u);
+      cd* buf = sbuf + st * STAGE;
+      if (backsub && arith) {
+        for (int c = h; c < 3; c += NSPLIT) {
+          if (live) {
+            cd q[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) q[k] = buf[sbase + 3 * k + c];
+            row_backsub<N>(q, buf + 2 * TILE);
+#pragma unroll
+            for (int k = 0; k < N; ++k) buf[sbase + 3 * k + c] = q[k];
+          }
+        }
+      }
+      __syncwarp();
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < JC; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) qh[c][j] = buf[sbase + 3 * (h * JC + j) + c];
+      }
+      fence_proxy_async();
+      mbar_arrive(computed + st);
+      ++it;
+    }
+    for (int s = 0; s < n_active; ++s, ++it) {
+      const int st = static_cast<int>(it & 1);
+      mbar_wait(full + st, static_cast<uint32_t>(it >> 1) & 1u);
+      cd* sP = sbuf + st * STAGE + sbase;
+      cd* sX = sP + TILE;
+      const cd* sA = sbuf + st * STAGE + 2 * TILE;
+      const cd* sB = sA + N * N;
+      cd acc[3][JC];
+      if (live && arith) {
+        // ---- X_s += P_s A_s ----
+#pragma unroll
+        for (int j = 0; j < JC; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c][j] = sX[3 * (h * JC + j) + c];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const cd p0 = sP[3 * k], p1 = sP[3 * k + 1], p2 = sP[3 * k + 2];
+#pragma unroll
+          for (int j = 0; j < JC; ++j) {
+            const cd m = lds_cd(sA + (k * JC + j) * NSPLIT + h);
+            cmac(acc[0][j], p0, m);
+            cmac(acc[1][j], p1, m);
+            cmac(acc[2][j], p2, m);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < JC; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) sX[3 * (h * JC + j) + c] = acc[c][j];
+        // ---- P_s <- P_s B_s + Q ----
+#pragma unroll
+        for (int j = 0; j < JC; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c][j] = czero();
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          const cd p0 = sP[3 * k], p1 = sP[3 * k + 1], p2 = sP[3 * k + 2];
+#pragma unroll
+          for (int j = 0; j < JC; ++j) {
+            const cd m = lds_cd(sB + (k * JC + j) * NSPLIT + h);
+            cmac(acc[0][j], p0, m);
+            cmac(acc[1][j], p1, m);
+            cmac(acc[2][j], p2, m);
+          }
+        }
+      }
+      __syncwarp();  // partner lanes have finished reading the P rows before they are overwritten
+      if (live && arith) {
+#pragma unroll
+        for (int j = 0; j < JC; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            sP[3 * (h * JC + j) + c] = cadd(acc[c][j], qh[c][j]);  // tmp = P*L ; tmp += Q (fields.hpp:85-86)
+      }
+      fence_proxy_async();
+      mbar_arrive(computed + st);
+    }
   }
 }
 

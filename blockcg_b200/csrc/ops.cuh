@@ -24,6 +24,10 @@ struct OpsTable {
   int (*shift_update)(cudaStream_t st, cd* Q, const ShiftPtrs* fp, const cd* R, const cd* A, const cd* B,
                       long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl, int sms,
                       int* launches);
+  // the same update with the first-generation register-direct kernel (kept for comparison)
+  int (*shift_update_direct)(cudaStream_t st, cd* Q, const ShiftPtrs* fp, const cd* R, const cd* A, const cd* B,
+                             long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl, int sms,
+                             int* launches);
   int (*max_partials)(int sms);
   void (*prepare)(int sms);  // occupancy queries / smem opt-in; call once outside stream capture
 };
@@ -57,11 +61,14 @@ struct Ops {
   static constexpr bool FUSED = DG::CAN_GRAM && AG::CAN_GRAM;
   static constexpr int GRAM_Y = (GramGeom<N>::NTASK + (kNT / 32) - 1) / (kNT / 32);
   static constexpr size_t SHIFT_SMEM = sizeof(cd) * 5 * N * N;
+  static constexpr int SHIFT_TS = 32;  // sites per pipeline tile
+  using SG = ShiftGeom<N, SHIFT_TS>;
+  static constexpr bool PIPE_OK = SG::SMEM_BYTES <= 227 * 1024;
 
   // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
   // outside any stream capture -- and used to size the persistent grids.
   struct Caps {
-    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0;
+    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0;
   };
   static Caps& caps() {
     static Caps c;
@@ -80,6 +87,7 @@ struct Ops {
     c.rescale = occupancy_blocks(rescale_add_kernel<N, kNT>, kNT, 0, sms);
     c.trsm = occupancy_blocks(trsm_kernel<N, kNT>, kNT, 0, sms);
     c.shift = occupancy_blocks(shift_update_kernel<N, kNT>, kNT, SHIFT_SMEM, sms);
+    if constexpr (PIPE_OK) c.pipe = occupancy_blocks(shift_pipe_kernel<N, SHIFT_TS>, SG::NT, SG::SMEM_BYTES, sms);
   }
 
   static int err() {
@@ -164,6 +172,20 @@ struct Ops {
                           long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl, int sms,
                           int* launches) {
     prepare(sms);
+    if constexpr (PIPE_OK) {
+      const int grid = clamp_grid((V + SHIFT_TS - 1) / SHIFT_TS, caps().pipe);
+      shift_pipe_kernel<N, SHIFT_TS><<<grid, SG::NT, SG::SMEM_BYTES, st>>>(Q, *fp, Rm, A, B, V, do_backsub,
+                                                                           n_active_fixed, ctrl);
+      if (launches) ++*launches;
+      return err();
+    }
+    return shift_update_direct(st, Q, fp, Rm, A, B, V, do_backsub, n_active_fixed, ctrl, sms, launches);
+  }
+
+  static int shift_update_direct(cudaStream_t st, cd* Q, const ShiftPtrs* fp, const cd* Rm, const cd* A,
+                                 const cd* B, long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl,
+                                 int sms, int* launches) {
+    prepare(sms);
     shift_update_kernel<N, kNT><<<clamp_grid((3 * V + kNT - 1) / kNT, caps().shift), kNT, SHIFT_SMEM, st>>>(
         Q, *fp, Rm, A, B, V, do_backsub, n_active_fixed, ctrl);
     if (launches) ++*launches;
@@ -185,6 +207,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::rescale_add,
                              &Ops<N>::trsm,
                              &Ops<N>::shift_update,
+                             &Ops<N>::shift_update_direct,
                              &Ops<N>::max_partials,
                              &Ops<N>::prepare};
   return &t;

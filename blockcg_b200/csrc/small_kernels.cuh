@@ -21,7 +21,7 @@ enum MatSlot {
   M_ALPHA_INV1,
   M_RHO0,        // rho, double-buffered likewise
   M_RHO1,
-  M_RHO_CUR,     // copy of the newest rho for the field kernels
+  M_RHO_CUR,     // newest rho with its diagonal inverted (operand of the in-kernel back substitution)
   M_DELTA,
   M_R2,          // BCG: r2 ; BCGrQ init: Gram of B
   M_R2_OLD,
@@ -385,7 +385,7 @@ rq_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm, 
     mats[L.fixed(M_DELTA) + e] = d;
     mats[L.fixed(M_RHO0) + e] = d;
     mats[L.fixed(M_RHO1) + e] = d;
-    mats[L.fixed(M_RHO_CUR) + e] = d;
+    mats[L.fixed(M_RHO_CUR) + e] = ((e % N) == (e / N)) ? cdiv(cmake(1.0, 0.0), d) : d;
     mats[L.fixed(M_ALPHA_INV0) + e] = id;
     mats[L.fixed(M_ALPHA_INV1) + e] = id;
     for (int sh = 0; sh < L.S; ++sh) {
@@ -448,7 +448,7 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
     ainv_g[e] = Ainv[e];
     mats[L.fixed(M_ALPHA) + e] = alpha[e];
     mats[L.fixed(M_NEGALPHA) + e] = cmake(-alpha[e].x, -alpha[e].y);
-    mats[L.A(0) + e] = ad[e];
+    mats[L.A(0) + shift_mat_index(N, e % N, e / N)] = ad[e];
   }
 }
 
@@ -485,9 +485,9 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
     for (int e = threadIdx.x; e < nn; e += blockDim.x) {
       const int i = e % N, j = e / N;
       rho_g[e] = rho[e];
-      mats[L.fixed(M_RHO_CUR) + e] = rho[e];
+      mats[L.fixed(M_RHO_CUR) + e] = (i == j) ? cdiv(cmake(1.0, 0.0), rho[e]) : rho[e];
       mats[L.fixed(M_DELTA) + e] = dn[e];
-      mats[L.B(0) + e] = cconj(rho[j + N * i]);
+      mats[L.B(0) + shift_mat_index(N, i, j)] = cconj(rho[j + N * i]);
     }
     if (threadIdx.x == 0) {
       double r = 0.0;
@@ -559,8 +559,8 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     mats[L.alpha_s(sh) + e] = t2[e];
     mats[L.beta_s(sh) + e] = beta[e];
-    mats[L.A(sh) + e] = t2[e];
-    mats[L.B(sh) + e] = t1[e];
+    mats[L.A(sh) + shift_mat_index(N, e % N, e / N)] = t2[e];
+    mats[L.B(sh) + shift_mat_index(N, e % N, e / N)] = t1[e];
   }
   if (threadIdx.x == 0) {
     double r = 0.0;
@@ -607,7 +607,7 @@ bcg_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpa
     const cd a = s.mat[1][e];
     mats[L.fixed(M_ALPHA) + e] = a;
     mats[L.fixed(M_NEGALPHA) + e] = cmake(-a.x, -a.y);
-    mats[L.A(0) + e] = a;
+    mats[L.A(0) + shift_mat_index(N, e % N, e / N)] = a;
   }
 }
 // B-step: r2_old = r2 ; r2 = R^dag R ; beta = LU(r2_old).solve(r2) ; residual ; B_0 = beta
@@ -628,7 +628,7 @@ bcg_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__
   sm_lu_solve(beta, r2old, s.lw, N);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     mats[L.fixed(M_R2) + e] = r2[e];
-    mats[L.B(0) + e] = beta[e];
+    mats[L.B(0) + shift_mat_index(N, e % N, e / N)] = beta[e];
   }
   if (threadIdx.x == 0) {
     double r = 0.0;

@@ -136,7 +136,8 @@ int bcg_solve_sbcgrq(bcg_ctx* ctx, double* const* x_host, const double* b_host, 
 /* ---- micro-benchmark hooks (timed on the context's stream with CUDA events) -------------- */
 /* Runs `reps` back-to-back launches of one kernel and returns the mean device
  * time per launch in *ms_out.  which: 0 dirac apply (+fused Gram), 1 dirac apply only,
- * 2 Gram, 3 Q -= T*alpha with fused Gram, 4 multishift update over n_shifts shifts,
+ * 2 Gram, 3 Q -= T*alpha with fused Gram, 4 multishift update over n_shifts shifts (7: its
+ * first-generation register-direct variant),
  * 5 X += P*M, 6 P = P*L + Q.  Fields are the context's own scratch, filled by the caller
  * through handles f0..f3 where needed. */
 int bcg_bench_kernel(bcg_ctx* ctx, int which, int reps, int n_shifts, const int* handles, int n_handles,

@@ -37,6 +37,7 @@ def run(V, N, S, reps, seed=0):
             ("rescale_add", 6, hs[:2], 1, 3 * F),
             ("shift_update_S%d" % S, 4, hs[:1 + 2 * S], S, (2 + 4 * S) * F),
             ("shift_update_S1", 4, hs[:3], 1, 6 * F),
+            ("shift_direct_S%d" % S, 7, hs[:1 + 2 * S], S, (2 + 4 * S) * F),
         ]
         for name, which, handles, ns, bytes_alg in kernels:
             ms, nl = ctx.bench_kernel(which, reps, handles, ns)
