@@ -22,6 +22,58 @@
 #include "ops.cuh"
 #include "small_kernels.cuh"
 
+// ---- NCCL is bound lazily with dlopen: no link-time dependency, so a single-GPU user never
+// loads it, and in a process that already mapped a libnccl.so.2 (e.g. the one bundled with
+// PyTorch) that very copy is reused instead of a second, possibly older, one.
+#include <dlfcn.h>
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.handle) return api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return api;
+  api.handle = h;
+#define BCG_SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, name))
+  BCG_SYM(GetUniqueId, "ncclGetUniqueId");
+  BCG_SYM(CommInitRank, "ncclCommInitRank");
+  BCG_SYM(CommDestroy, "ncclCommDestroy");
+  BCG_SYM(AllReduce, "ncclAllReduce");
+  BCG_SYM(Send, "ncclSend");
+  BCG_SYM(Recv, "ncclRecv");
+  BCG_SYM(GroupStart, "ncclGroupStart");
+  BCG_SYM(GroupEnd, "ncclGroupEnd");
+  BCG_SYM(GetErrorString, "ncclGetErrorString");
+#undef BCG_SYM
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv &&
+           api.GroupStart && api.GroupEnd && api.GetErrorString;
+  return api;
+}
+}  // namespace
+#define ncclGetUniqueId nccl_api().GetUniqueId
+#define ncclCommInitRank nccl_api().CommInitRank
+#define ncclCommDestroy nccl_api().CommDestroy
+#define ncclAllReduce nccl_api().AllReduce
+#define ncclSend nccl_api().Send
+#define ncclRecv nccl_api().Recv
+#define ncclGroupStart nccl_api().GroupStart
+#define ncclGroupEnd nccl_api().GroupEnd
+#define ncclGetErrorString nccl_api().GetErrorString
+
 namespace bcg {
 #define BCG_DECL(n) const OpsTable* get_ops_##n();
 BCG_FOR_EACH_N(BCG_DECL)
@@ -330,6 +382,7 @@ int bcg_ctx_destroy(bcg_ctx* c) {
 int bcg_comm_get_unique_id(void* id_out) {
   static_assert(sizeof(ncclUniqueId) <= BCG_UNIQUE_ID_BYTES, "id size");
   if (!id_out) return BCG_ERR_INVALID;
+  if (!nccl_api().ok) return BCG_ERR_NCCL;
   ncclUniqueId id;
   if (ncclGetUniqueId(&id) != ncclSuccess) return BCG_ERR_NCCL;
   std::memset(id_out, 0, BCG_UNIQUE_ID_BYTES);
@@ -339,6 +392,7 @@ int bcg_comm_get_unique_id(void* id_out) {
 
 int bcg_comm_init(bcg_ctx* c, const void* id_in) {
   if (!c || !id_in) return BCG_ERR_INVALID;
+  if (!nccl_api().ok) return fail(c, BCG_ERR_NCCL, "libnccl.so.2 could not be loaded");
   CU(cudaSetDevice(c->device));
   ncclUniqueId id;
   std::memcpy(&id, id_in, sizeof id);

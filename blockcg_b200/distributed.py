@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing: one process per GPU, contiguous site slabs (for V = L^3 x T this is the
+t-slab split), torch.distributed only to agree on the NCCL id and to move test data.
+
+The data path itself lives in the CUDA library: halo exchange (2 sites per side for the
+reference's 1-D operator) and the N x N Gram all-reduce run on the library's own
+communicator and stream (blockcg_b200/csrc/capi.cu: halo_refresh, gram_finalize).
+"""
+import numpy as np
+
+from .capi import UNIQUE_ID_BYTES, Context
+
+HALO = 2  # op = m^2 - D^2 reaches x +- 2 (inc/dirac_op.hpp:14-21,36-43)
+
+
+def slab_range(V, rank, nranks):
+    """[begin, end) of the contiguous site range owned by `rank` (V must divide evenly)."""
+    if V % nranks:
+        raise ValueError("V=%d is not divisible by %d ranks" % (V, nranks))
+    if V // nranks < HALO:
+        raise ValueError("need at least %d sites per rank" % HALO)
+    n = V // nranks
+    return rank * n, (rank + 1) * n
+
+
+def neighbours(rank, nranks):
+    return (rank - 1) % nranks, (rank + 1) % nranks
+
+
+def halo_sources(V, rank, nranks):
+    """Global site indices whose values fill this rank's halo slots [-2,-1] and [Vl, Vl+1]."""
+    b, e = slab_range(V, rank, nranks)
+    return [(b - 2) % V, (b - 1) % V], [e % V, (e + 1) % V]
+
+
+def broadcast_unique_id(dist, device=None):
+    """Rank 0 creates the library's NCCL id, everybody receives it (any torch backend)."""
+    import torch
+    buf = torch.zeros(UNIQUE_ID_BYTES, dtype=torch.uint8)
+    if dist.get_rank() == 0:
+        buf = torch.frombuffer(bytearray(Context.unique_id()), dtype=torch.uint8).clone()
+    if device is not None:
+        buf = buf.to(device)
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def make_context(dist, V, N, max_shifts, device, U_global, mass):
+    """Slab context of this rank, communicator initialised, links (own slab) uploaded."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    b, e = slab_range(V, rank, world)
+    ctx = Context(e - b, N, max_shifts=max_shifts, device=device, rank=rank, nranks=world)
+    import torch
+    uid = broadcast_unique_id(dist, torch.device("cuda", device) if dist.get_backend() == "nccl" else None)
+    ctx.comm_init(uid)
+    ctx.set_links(np.ascontiguousarray(U_global[b:e]), mass)
+    return ctx, (b, e)
