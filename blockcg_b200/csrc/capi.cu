@@ -105,6 +105,7 @@ struct GraphCache {
 struct bcg_ctx {
   int device = 0, rank = 0, nranks = 1;
   long long V = 0;
+  long long cap = 0;  // allocated sites after site 0 (>= V + 2), see OpsTable::field_capacity
   int N = 0, S = 1, sms = 0;
   double mass = 0.0;
   bool links_set = false;
@@ -169,7 +170,7 @@ int fail(bcg_ctx* c, int code, const char* fmt, ...) {
   } while (0)
 
 inline size_t site_elems(const bcg_ctx* c) { return static_cast<size_t>(3) * c->N; }
-inline size_t field_elems(const bcg_ctx* c) { return static_cast<size_t>(c->V + 4) * site_elems(c); }
+inline size_t field_elems(const bcg_ctx* c) { return static_cast<size_t>(c->cap + 2) * site_elems(c); }
 inline cd* fptr(const bcg_ctx* c, int h) { return c->fields[h] + 2 * site_elems(c); }
 inline cd* uptr(const bcg_ctx* c) { return c->U_alloc + 2 * 9; }
 inline bool valid(const bcg_ctx* c, int h) {
@@ -322,6 +323,7 @@ int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, in
                 prop.minor);
   c->sms = prop.multiProcessorCount;
   c->ops->prepare(c->sms);
+  c->cap = c->ops->field_capacity(c->V, c->sms);
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->L.N = n_rhs;
   c->L.S = max_shifts;
@@ -335,7 +337,8 @@ int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, in
   CU(cudaMemset(c->ctrl, 0, sizeof(Ctrl)));
   CU(cudaMallocHost(&c->ctrl_host, 2 * sizeof(Ctrl)));
   CU(cudaMallocHost(&c->mat_host, 4 * c->L.nn() * sizeof(cd)));
-  CU(cudaMalloc(&c->U_alloc, static_cast<size_t>(c->V + 4) * 9 * sizeof(cd)));
+  CU(cudaMalloc(&c->U_alloc, static_cast<size_t>(c->cap + 2) * 9 * sizeof(cd)));
+  CU(cudaMemset(c->U_alloc, 0, static_cast<size_t>(c->cap + 2) * 9 * sizeof(cd)));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   for (auto& e : c->ev_batch) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   c->small_smem = SmallSmem::bytes(n_rhs);
@@ -928,6 +931,12 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         break;
       case 1:
         KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, nullptr, nullptr, c->sms, l));
+        break;
+      case 9:  // first-generation stencil (+ fused Gram), kept for comparison
+        KL(c->ops->dirac_v1(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, c->gpart, nullptr, c->sms, l));
+        break;
+      case 10:
+        KL(c->ops->dirac_v1(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, nullptr, nullptr, c->sms, l));
         break;
       case 2:
         KL(c->ops->gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), c->V, c->gpart, nullptr, c->sms, l));

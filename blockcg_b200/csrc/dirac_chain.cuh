@@ -1,0 +1,354 @@
+// K1 (second generation): block Dirac apply as a warp-specialised parity-chain pipeline.
+//
+// Operator (reference inc/dirac_op.hpp:14-21,36-43; shift term block_solvers.hpp:136):
+//   D v[x] = 1/2 U[x] v[x+1] - 1/2 U[x-1]^dag v[x-1],   T = (m^2 + sigma) P - D(D P)
+// T[x] only couples to P[x-2], P[x], P[x+2]: the even and the odd sub-lattice are closed
+// under the operator.  A stencil thread therefore walks a *parity chain* x, x+2, x+4, ...
+// for a group of R right-hand sides and keeps (D P)[x-1] of the in-between site in
+// registers from one step to the next:
+//     tp     = 1/2 (U[x+1] P[x+2] - U[x]^dag P[x])            = (D P)[x+1]
+//     T[x]   = (m^2+sigma) P[x] - 1/2 (U[x] tp - U[x-1]^dag tm)        tm = (D P)[x-1]
+//     tm <- tp ; x <- x + 2
+// so D P is computed exactly once per site and never stored anywhere, and every P / T
+// element crosses shared memory once (the first-generation kernel moved 2.5x as much
+// through shared memory, which -- not HBM -- was what bound it).
+//
+// CTA = one SM, persistent:
+//   NSW stencil warps : lane = (column group g, parity p, sub-chain k').  The CTA owns K
+//                       sub-chains (contiguous site ranges); every tile advances each of
+//                       them by W sites.
+//   4 Gram warps      : a quarter of the lower triangle of P^dag T each (GramPart), over the
+//                       rows of the finished tile, accumulated in registers over the whole kernel, one partial N x N
+//                       block per CTA at the end (fixed order => deterministic).
+//   1 loader warp     : cp.async.bulk (SASS UBLKCP) of the P / U windows, PF tiles ahead.
+//   1 storer warp     : bulk stores of the T windows.
+// Hand-off is by mbarriers only (inb: TMA -> stencil, ofull: stencil -> Gram + storer,
+// gdone: Gram -> loader + stencil, sdone: storer -> stencil); no __syncthreads in the loop.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "field_kernels.cuh"
+
+namespace bcg {
+
+// ---- balanced four-way split of the lower triangle of an N x N Gram block (N even, H = N/2) ----
+//   part 0: rows [0,H)      x cols [0,H)  lower triangle      part 1: rows [H,H+H1)  x cols [0,H)
+//   part 3: rows [H,N)      x cols [H,N)  lower triangle      part 2: rows [H+H1,N)  x cols [0,H)
+// H(H+1)/2, H1*H, (H-H1)*H, H(H+1)/2 entries: 21/18/18/21 at N = 12 -- one warp per part, one
+// warp per SM sub-partition, so the FP64 work of the Gram is spread evenly over the four
+// schedulers.  Only entries with row >= col are produced (fields.hpp:103-122).
+template <int N, int PART>
+struct GramPart {
+  static_assert(N % 2 == 0, "GramPart needs an even N");
+  static constexpr int H = N / 2, H1 = (H + 1) / 2;
+  static constexpr int R0 = (PART == 0) ? 0 : (PART == 1) ? H : (PART == 2) ? H + H1 : H;
+  static constexpr int NR = (PART == 0) ? H : (PART == 1) ? H1 : (PART == 2) ? H - H1 : H;
+  static constexpr int C0 = (PART == 3) ? H : 0;
+  static constexpr int NC = H;
+  static constexpr bool LOWER = (PART == 0 || PART == 3);
+  cd acc[NR > 0 ? NR : 1][NC];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[i][j] = czero();
+  }
+  // one row (site, colour): pa / pb point at column 0 of the row in A / B, columns 3 apart
+  __device__ __forceinline__ void row(const cd* __restrict__ pa, const cd* __restrict__ pb) {
+    cd a[NR > 0 ? NR : 1], b[NC];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) a[i] = pa[3 * (R0 + i)];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) b[j] = pb[3 * (C0 + j)];
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (!LOWER || j <= i) cmac_conj(acc[i][j], a[i], b[j]);
+  }
+  // xor-tree over the lanes (fixed order), lane 0 writes its entries of the N x N column-major block
+  __device__ __forceinline__ void store(cd* __restrict__ dstNN) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        if (LOWER && j > i) continue;
+        double re = acc[i][j].x, im = acc[i][j].y;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          re += __shfl_xor_sync(0xffffffffu, re, off);
+          im += __shfl_xor_sync(0xffffffffu, im, off);
+        }
+        if ((threadIdx.x & 31) == 0) dstNN[(R0 + i) + N * (C0 + j)] = cmake(re, im);
+      }
+  }
+};
+
+// ---- tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) ----------------------------
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+               "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
+               : "memory");
+}
+
+template <int N, int G, int K, int W>
+struct ChainGeom {
+  static_assert(N % G == 0, "G must divide N");
+  static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16, "G must be a power of two <= 16");
+  static_assert(W % 2 == 0 && W >= 2, "window must hold whole parity pairs");
+  static constexpr int R = N / G;                 // rhs columns per stencil thread
+  static constexpr int SITE = 3 * N;              // complex per site
+  static constexpr int KW = 16 / G;               // sub-chains per stencil warp
+  static_assert(K % KW == 0, "K must fill whole warps");
+  static constexpr int NSW = K / KW;              // stencil warps
+  static constexpr int NGW = 4;                   // Gram warps: one GramPart each, one per SM sub-partition
+  static constexpr int NWARPS = NSW + NGW + 2;
+  static constexpr int NT = NWARPS * 32;
+  static constexpr int WARP_LOAD = NSW + NGW, WARP_STORE = NSW + NGW + 1;
+  // window pitches in complex (16-byte) units: field windows start on residues 0,1,2,.. mod 8
+  // (conflict-free Gram rows), link windows on residues 0,6,4,2 (conflict-free link broadcast)
+  static constexpr int PP = W * SITE + ((1 - (W * SITE) % 8 + 8) % 8);
+  static constexpr int PU = (W + 2) * 9 + ((6 - ((W + 2) * 9) % 8 + 8) % 8);
+  static constexpr int SP = 5, SU = 4, SO = 2;    // ring depths: P windows, link windows, T windows
+  static constexpr int NBAR_IN = 4, NBAR_G = 4;
+  static constexpr int P_ELEMS = SP * K * PP, U_ELEMS = SU * K * PU, O_ELEMS = SO * K * PP;
+  static constexpr size_t SMEM_BYTES =
+      sizeof(cd) * (P_ELEMS + U_ELEMS + O_ELEMS) + 8 * (NBAR_IN + 2 + NBAR_G + 2) + 16;
+  static constexpr int ROWS = 3 * K * W;          // Gram rows per tile
+  // lanes of a quarter warp must hit 8 distinct 16-byte bank groups when they read their P
+  // columns: when consecutive sites are 4 (mod 8) units apart the parity bit goes inside
+  // the quarter warp, otherwise a sub-chain bit does (windows are 1 (mod 8) apart).
+  static constexpr bool PARITY_INNER = (G != 4) || (SITE % 8 == 4);
+};
+
+template <int N, int G, int K, int W, bool GRAM>
+__global__ void __launch_bounds__(ChainGeom<N, G, K, W>::NT, 1)
+dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmO,
+                   const __grid_constant__ CUtensorMap tmU, const cd* __restrict__ in,
+                   const cd* __restrict__ U, long long V, long long L, double m2, double sigma,
+                   cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl) {
+  using Geo = ChainGeom<N, G, K, W>;
+  constexpr int R = Geo::R, SITE = Geo::SITE, PP = Geo::PP, PU = Geo::PU;
+  constexpr int SP = Geo::SP, SU = Geo::SU, SO = Geo::SO;
+  if (ctrl != nullptr && (ctrl->done | ctrl->stop)) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cd* sP = reinterpret_cast<cd*>(smem_raw);
+  cd* sU = sP + Geo::P_ELEMS;
+  cd* sO = sU + Geo::U_ELEMS;
+  uint64_t* inb = reinterpret_cast<uint64_t*>(sO + Geo::O_ELEMS);
+  uint64_t* ofull = inb + Geo::NBAR_IN;
+  uint64_t* gdone = ofull + 2;
+  uint64_t* sdone = gdone + Geo::NBAR_G;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < Geo::NBAR_IN; ++i) mbar_init(inb + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(ofull + i, Geo::NSW);
+    for (int i = 0; i < Geo::NBAR_G; ++i) mbar_init(gdone + i, GRAM ? Geo::NGW : Geo::NSW);
+    for (int i = 0; i < 2; ++i) mbar_init(sdone + i, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int T = static_cast<int>(L / W);                      // tiles
+  const long long chain0 = static_cast<long long>(blockIdx.x) * K;  // first sub-chain of this CTA
+  // sub-chain q covers out sites [q*L, min((q+1)*L, V))
+  auto chain_start = [&](int k) { return (chain0 + k) * L; };
+  auto chain_end = [&](int k) {
+    const long long e = (chain0 + k + 1) * L;
+    return e < V ? e : V;
+  };
+
+  constexpr uint32_t P_BOX_BYTES = K * PP * sizeof(cd), U_BOX_BYTES = K * PU * sizeof(cd);
+  const int q0 = static_cast<int>(chain0);
+
+  if (warp == Geo::WARP_LOAD) {
+    // ===================== loader: three tensor copies per tile, one elected lane =====================
+    // input barrier of tile t covers P-load t+1 (sites o0+W .. o0+2W) and link-load t
+    // (links o0-1 .. o0+W+1) of all K sub-chains; tile 0 also brings P-load 0.
+    // Window j of sub-chain q is box row (j, q) of the 3-D view (see make_chain_maps):
+    // the view is flat in (window, chain), so window T of chain q is window 0 of chain q+1.
+    if (lane != 0) return;
+    for (int t = 0; t < T; ++t) {
+      if (t >= 4) mbar_wait(gdone + (t & 3), static_cast<uint32_t>(((t - 4) >> 2) & 1));
+      uint64_t* bar = inb + (t & 3);
+      mbar_arrive_expect_tx(bar, (t == 0 ? 2u : 1u) * P_BOX_BYTES + U_BOX_BYTES);
+      if (t == 0) tma_load_3d(sP, &tmP, 0, 0, q0, bar);
+      const int j = t + 1;
+      tma_load_3d(sP + (j % SP) * (K * PP), &tmP, 0, j == T ? 0 : j, j == T ? q0 + 1 : q0, bar);
+      tma_load_3d(sU + (t % SU) * (K * PU), &tmU, 0, t, q0, bar);
+    }
+    return;
+  }
+
+  if (warp == Geo::WARP_STORE) {
+    // ===================== storer: one tensor store per tile =====================
+    // the pad element of every window row lies outside dimension 0 of the view: not written
+    if (lane != 0) return;
+    for (int t = 0; t < T; ++t) {
+      mbar_wait(ofull + (t & 1), static_cast<uint32_t>((t >> 1) & 1));
+      tma_store_3d(&tmO, 0, t, q0, sO + (t % SO) * (K * PP));
+      bulk_commit();
+      bulk_wait_read0();  // shared memory of this tile has been read
+      mbar_arrive(sdone + (t & 1));
+    }
+    bulk_wait0();
+    return;
+  }
+
+  if (warp >= Geo::NSW) {
+    // ===================== Gram warps: block (ti,tj) of P^dag T =====================
+    if (!GRAM) return;
+    // row = (colour c, site s of the window, sub-chain k), k fastest across lanes: the 8 lanes of a
+    // quarter warp read 8 consecutive windows, which start on 8 different 16-byte bank groups
+    auto gram_loop = [&](auto& part) {
+      part.init();
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(ofull + (t & 1), static_cast<uint32_t>((t >> 1) & 1));
+        const cd* tP = sP + (t % SP) * (K * PP);  // P-load t holds P at this tile's out sites
+        const cd* tO = sO + (t % SO) * (K * PP);
+#pragma unroll
+        for (int it = 0; it < (Geo::ROWS + 31) / 32; ++it) {
+          const int rr = lane + 32 * it;
+          const int k = rr % K, s = (rr / K) % W, c = rr / (K * W);
+          const long long rem = chain_end(k) - chain_start(k);  // sites of sub-chain k (<= 0: empty)
+          if (rr < Geo::ROWS && t * W + s < rem) {
+            const int base = k * PP + s * SITE + c;
+            part.row(tP + base, tO + base);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gdone + (t & 3));
+      }
+      part.store(gpart + static_cast<size_t>(blockIdx.x) * N * N);
+    };
+    switch (warp - Geo::NSW) {
+      case 0: { GramPart<N, 0> part; gram_loop(part); break; }
+      case 1: { GramPart<N, 1> part; gram_loop(part); break; }
+      case 2: { GramPart<N, 2> part; gram_loop(part); break; }
+      default: { GramPart<N, 3> part; gram_loop(part); break; }
+    }
+    return;
+  }
+
+  // ===================== stencil warps =====================
+  int g, p, kq;
+  {
+    const int l8 = lane & 7, q8 = lane >> 3;
+    if (G == 4) {
+      g = l8 & 3;
+      if (Geo::PARITY_INNER) {
+        p = l8 >> 2;
+        kq = q8;
+      } else {
+        p = q8 & 1;
+        kq = (q8 >> 1) * 2 + (l8 >> 2);
+      }
+    } else {
+      g = lane % G;
+      p = (lane / G) & 1;
+      kq = lane / (2 * G);
+    }
+  }
+  const int k = warp * Geo::KW + kq;
+  const long long cs = chain_start(k);
+  const long long rem_ll = chain_end(k) - cs;
+  const int rem = rem_ll < 0 ? 0 : static_cast<int>(rem_ll);  // valid out sites of this sub-chain
+  const int col0 = g * R * 3;  // first complex of this thread's columns inside a site
+  const double ms = m2;
+
+  cd tm[R][3];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tm[r][c] = czero();
+  if (p < rem) {
+    // chain start: (D P)[x-1] for the first site of this chain, straight from global memory
+    const long long x = cs + p;
+    cd v[R][3], acc[R][3];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[r][c] = czero();
+    load_cols<N, R>(in + x * SITE + col0, v);
+    apply_link<R>(U + (x - 1) * 9, v, acc);
+    load_cols<N, R>(in + (x - 2) * SITE + col0, v);
+    apply_link_dag_sub<R>(U + (x - 2) * 9, v, acc);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tm[r][c] = cscale(acc[r][c], 0.5);
+  }
+
+  for (int t = 0; t < T; ++t) {
+    mbar_wait(inb + (t & 3), static_cast<uint32_t>((t >> 2) & 1));
+    if (t >= 2) {  // T window slot free again: Gram and store of tile t-2 are through with it
+      if (GRAM) mbar_wait(gdone + ((t - 2) & 3), static_cast<uint32_t>(((t - 2) >> 2) & 1));
+      mbar_wait(sdone + (t & 1), static_cast<uint32_t>(((t - 2) >> 1) & 1));
+    }
+    const cd* tP0 = sP + (t % SP) * (K * PP) + k * PP;         // P at out sites o0 .. o0+W
+    const cd* tP1 = sP + ((t + 1) % SP) * (K * PP) + k * PP;   // P at o0+W .. o0+2W
+    const cd* tU = sU + (t % SU) * (K * PU) + k * PU;          // links o0-1 .. o0+W+1
+    cd* tO = sO + (t % SO) * (K * PP) + k * PP;
+#pragma unroll
+    for (int i = 0; i < W / 2; ++i) {
+      const int ls = p + 2 * i;  // out site o0 + ls
+      cd v[R][3], tp[R][3], acc[R][3];
+      // tp = 1/2 (U[x+1] P[x+2] - U[x]^dag P[x])
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[r][c] = czero();
+      load_cols<N, R>((ls + 2 < W ? tP0 + (ls + 2) * SITE : tP1 + (ls + 2 - W) * SITE) + col0, v);
+      apply_link<R>(tU + (ls + 2) * 9, v, acc);
+      load_cols<N, R>(tP0 + ls * SITE + col0, v);
+      apply_link_dag_sub<R>(tU + (ls + 1) * 9, v, acc);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tp[r][c] = cscale(acc[r][c], 0.5);
+      // T[x] = (m^2 + sigma) P[x] - 1/2 (U[x] tp - U[x-1]^dag tm)
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[r][c] = czero();
+      apply_link<R>(tU + (ls + 1) * 9, tp, acc);
+      apply_link_dag_sub<R>(tU + ls * 9, tm, acc);
+      {  // sites past the end of the field land in the allocation slack (never read back)
+        cd* o = tO + ls * SITE + col0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            // lhs = -D(D rhs) + m^2 rhs (dirac_op.hpp:42), then += sigma rhs (block_solvers.hpp:136)
+            cd tt = cmake(fma(ms, v[r][c].x, -0.5 * acc[r][c].x), fma(ms, v[r][c].y, -0.5 * acc[r][c].y));
+            tt.x = fma(sigma, v[r][c].x, tt.x);
+            tt.y = fma(sigma, v[r][c].y, tt.y);
+            o[r * 3 + c] = tt;
+          }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tm[r][c] = tp[r][c];
+    }
+    fence_proxy_async();  // T window visible to the bulk store
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(ofull + (t & 1));
+      if (!GRAM) mbar_arrive(gdone + (t & 3));  // no Gram warps: the stencil releases the input slots itself
+    }
+  }
+}
+
+}  // namespace bcg

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "field_kernels.cuh"
+#include "dirac_chain.cuh"
 
 namespace bcg {
 
@@ -14,6 +15,9 @@ struct OpsTable {
   // or a negative cudaError_t.
   int (*dirac)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
                cd* gpart, const Ctrl* ctrl, int sms, int* launches);
+  // first-generation tile kernel (intermediate staged in shared memory), kept for comparison
+  int (*dirac_v1)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
+                  cd* gpart, const Ctrl* ctrl, int sms, int* launches);
   int (*gram)(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
               int* launches);
   int (*axpy_gram)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
@@ -29,10 +33,48 @@ struct OpsTable {
                              long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl, int sms,
                              int* launches);
   int (*max_partials)(int sms);
+  // sites that must be allocated after site 0 of every field / of the links (>= V + 2): the
+  // tensor-map views of the chain stencil are rectangular and reach past the end of the field
+  long long (*field_capacity)(long long V, int sms);
   void (*prepare)(int sms);  // occupancy queries / smem opt-in; call once outside stream capture
 };
 
 const OpsTable* get_ops(int N);  // nullptr if N is not compiled in
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// 3-D view (window, tile, sub-chain) of a site-major array, all sizes in complex numbers:
+// window = win complex (dimension 0, contiguous), consecutive windows win_stride apart, sub-chain
+// rows row_stride = T * win_stride apart (the view is flat in (tile, chain)); box = K rows of `box`
+// complex each.  box > win pads every row in shared memory: the surplus elements are outside
+// dimension 0, i.e. zero-filled on load and not written on store.
+inline int make_chain_map(CUtensorMap* m, const cd* base, int win, int win_stride, int box, long long T,
+                          long long rows, int K) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return -static_cast<int>(cudaErrorNotSupported);
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(2 * win), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(win_stride) * sizeof(cd),
+                                 static_cast<cuuint64_t>(win_stride) * sizeof(cd) * static_cast<cuuint64_t>(T)};
+  const cuuint32_t bx[3] = {static_cast<cuuint32_t>(2 * box), 1u, static_cast<cuuint32_t>(K)};
+  const cuuint32_t es[3] = {1u, 1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<cd*>(base), dims, strides, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(cudaErrorInvalidValue);
+}
 
 #ifdef BCG_N  // ---- per-N implementation, included only by inst.cu ----------------------------
 
@@ -42,6 +84,10 @@ template <int N>
 struct Tune {
   // rhs columns per stencil work item (must divide N)
   static constexpr int R = (N % 3 == 0) ? 3 : (N % 2 == 0) ? 2 : 1;
+  // parity-chain stencil (dirac_chain.cuh): column groups per site, 0 = not used at this N
+  static constexpr int CHAIN_G = (N % 4 == 0 && N <= 12) ? 4 : 0;
+  static constexpr int CHAIN_K = 16;  // sub-chains per CTA
+  static constexpr int CHAIN_W = 2;   // sites per sub-chain and tile
 };
 
 template <typename K>
@@ -64,6 +110,9 @@ struct Ops {
   static constexpr int SHIFT_TS = 32;  // sites per pipeline tile
   using SG = ShiftGeom<N, SHIFT_TS>;
   static constexpr bool PIPE_OK = SG::SMEM_BYTES <= 227 * 1024;
+  static constexpr bool CHAIN = Tune<N>::CHAIN_G > 0;
+  static constexpr int CG_ = CHAIN ? Tune<N>::CHAIN_G : 1, CK = Tune<N>::CHAIN_K, CW = Tune<N>::CHAIN_W;
+  using CGm = ChainGeom<N, CG_, CHAIN ? CK : 16 / CG_, CW>;
 
   // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
   // outside any stream capture -- and used to size the persistent grids.
@@ -88,6 +137,36 @@ struct Ops {
     c.trsm = occupancy_blocks(trsm_kernel<N, kNT>, kNT, 0, sms);
     c.shift = occupancy_blocks(shift_update_kernel<N, kNT>, kNT, SHIFT_SMEM, sms);
     if constexpr (PIPE_OK) c.pipe = occupancy_blocks(shift_pipe_kernel<N, SHIFT_TS>, SG::NT, SG::SMEM_BYTES, sms);
+    if constexpr (CHAIN) {
+      cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)CGm::SMEM_BYTES);
+      cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)CGm::SMEM_BYTES);
+    }
+  }
+
+  // one persistent CTA per SM; the CTA's K sub-chains are contiguous ranges of L sites (T tiles of W)
+  struct ChainPlan {
+    int grid;
+    long long L, T, nchains;
+  };
+  static ChainPlan chain_plan(long long V, int sms) {
+    ChainPlan p;
+    const long long per_tile = static_cast<long long>(CK) * CW;
+    p.grid = clamp_grid((V + per_tile - 1) / per_tile, sms);
+    p.nchains = static_cast<long long>(p.grid) * CK;
+    p.L = (V + p.nchains - 1) / p.nchains;
+    p.L = (p.L + CW - 1) / CW * CW;
+    p.T = p.L / CW;
+    return p;
+  }
+  static long long field_capacity(long long V, int sms) {
+    if constexpr (CHAIN) {
+      const ChainPlan p = chain_plan(V, sms);
+      const long long cap = (p.nchains + 1) * p.L + CW + 2;
+      return cap > V + 2 ? cap : V + 2;
+    }
+    return V + 2;
   }
 
   static int err() {
@@ -111,6 +190,29 @@ struct Ops {
 
   static int dirac(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
                    cd* gpart, const Ctrl* ctrl, int sms, int* launches) {
+    if constexpr (CHAIN) {
+      prepare(sms);
+      const ChainPlan pl = chain_plan(V, sms);
+      alignas(64) CUtensorMap tmP, tmO, tmU;
+      int e = make_chain_map(&tmP, in, CW * 3 * N, CW * 3 * N, CGm::PP, pl.T, pl.nchains + 1, CK);
+      if (!e) e = make_chain_map(&tmO, out, CW * 3 * N, CW * 3 * N, CGm::PP, pl.T, pl.nchains + 1, CK);
+      if (!e) e = make_chain_map(&tmU, U - 9, (CW + 2) * 9, CW * 9, CGm::PU, pl.T, pl.nchains + 1, CK);
+      if (e) return e;
+      if (gpart != nullptr)
+        dirac_chain_kernel<N, CG_, CK, CW, true><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
+            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl);
+      else
+        dirac_chain_kernel<N, CG_, CK, CW, false><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
+            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl);
+      if (launches) ++*launches;
+      e = err();
+      return e ? e : (gpart != nullptr ? pl.grid : 0);
+    }
+    return dirac_v1(st, in, out, U, V, m2, sigma, gpart, ctrl, sms, launches);
+  }
+
+  static int dirac_v1(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
+                      cd* gpart, const Ctrl* ctrl, int sms, int* launches) {
     prepare(sms);
     const long long ntiles = (V + DG::TS - 1) / DG::TS;
     if (gpart != nullptr) {
@@ -202,6 +304,7 @@ const OpsTable* make_ops() {
                              DiracGeom<N, Tune<N>::R, kNT>::TS,
                              Ops<N>::FUSED ? 1 : 0,
                              &Ops<N>::dirac,
+                             &Ops<N>::dirac_v1,
                              &Ops<N>::gram,
                              &Ops<N>::axpy_gram,
                              &Ops<N>::rescale_add,
@@ -209,6 +312,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::shift_update,
                              &Ops<N>::shift_update_direct,
                              &Ops<N>::max_partials,
+                             &Ops<N>::field_capacity,
                              &Ops<N>::prepare};
   return &t;
 }

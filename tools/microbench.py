@@ -31,6 +31,8 @@ def run(V, N, S, reps, seed=0):
         kernels = [
             ("dirac_gram", 0, hs[:2], 1, 2 * F + Ub),
             ("dirac", 1, hs[:2], 1, 2 * F + Ub),
+            ("dirac_gram_v1", 9, hs[:2], 1, 2 * F + Ub),
+            ("dirac_v1", 10, hs[:2], 1, 2 * F + Ub),
             ("gram", 2, hs[:2], 1, 2 * F),
             ("axpy_gram", 3, hs[:2], 1, 3 * F),
             ("axpy", 5, hs[:2], 1, 3 * F),
