@@ -1,0 +1,188 @@
+// K3 (second generation): Q += T*M with the Gram Q^dag Q of the updated rows fused in, as a
+// warp-specialised tensor-map TMA pipeline (reference: block_fermion_field::add, inc/fields.hpp:70-77,
+// followed by hermitian_dot of the result, inc/fields.hpp:103-122,142; call sites
+// block_solvers.hpp:148-152 / :33-35).
+//
+// CTA = one SM, persistent, tiles of TS consecutive sites:
+//   1 loader lane   : two tensor copies per tile (T tile, Q tile).  The fields are viewed as
+//                     [site pair][2 * 3N complex] with a box one complex wider than a pair, so
+//                     every pair lands in shared memory one 16-byte word further round the banks
+//                     (the surplus element is out of bounds: zero on load, skipped on store).
+//   NCW update warps: a site is owned by NSPLIT lanes, lane h producing JC = N/NSPLIT columns for
+//                     the three colour rows; Q is updated in place in the stage buffer.
+//   4 Gram warps    : a quarter of the lower triangle of Q^dag Q each (GramPart) over the
+//                     finished tile; one partial N x N block per CTA at the end.
+//   1 storer lane   : one tensor store per tile.
+// Four stages; hand-off by mbarriers only.
+#pragma once
+#include "common.cuh"
+#include "dirac_chain.cuh"
+
+namespace bcg {
+
+template <int N, int TS>
+struct AxpyPipeGeom {
+  static_assert(N % 2 == 0 && N >= 4, "pipeline variant needs an even N >= 4");
+  static constexpr int NSPLIT = shift_nsplit(N);
+  static constexpr int JC = N / NSPLIT;
+  static constexpr int SPW = 32 / NSPLIT;            // sites per update warp
+  static_assert(TS % SPW == 0 && TS % 2 == 0, "tile must fill whole warps and whole pairs");
+  static constexpr int NCW = TS / SPW;               // update warps
+  static constexpr int NGW = 4;
+  static constexpr int NWARPS = NCW + NGW + 2;
+  static constexpr int NT = NWARPS * 32;
+  static constexpr int WARP_LOAD = NCW + NGW, WARP_STORE = NCW + NGW + 1;
+  static constexpr int SITE = 3 * N;
+  static constexpr int PAIR = 2 * SITE + ((1 - (2 * SITE) % 8 + 8) % 8);  // pair pitch, 1 (mod 8)
+  static constexpr int TILE = (TS / 2) * PAIR;       // complex per staged field tile
+  static constexpr int NSTAGE = 4;
+  static constexpr int STAGE = 2 * TILE;             // T tile, Q tile
+  static constexpr size_t SMEM_BYTES = sizeof(cd) * (NSTAGE * STAGE + N * N) + 8 * 4 * NSTAGE + 16;
+  static constexpr int ROWS = 3 * TS;
+};
+
+template <int N, int TS, bool GRAM>
+__global__ void __launch_bounds__(AxpyPipeGeom<N, TS>::NT, 1)
+axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT,
+                 const cd* __restrict__ M, long long V, cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl) {
+  using Geo = AxpyPipeGeom<N, TS>;
+  constexpr int NSPLIT = Geo::NSPLIT, JC = Geo::JC, SPW = Geo::SPW, NCW = Geo::NCW, SITE = Geo::SITE;
+  constexpr int PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE, NS = Geo::NSTAGE;
+  if (ctrl != nullptr && ctrl->done) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cd* sbuf = reinterpret_cast<cd*>(smem_raw);
+  cd* sM = sbuf + NS * STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sM + N * N);
+  uint64_t* cdone = full + NS;
+  uint64_t* gdone = cdone + NS;
+  uint64_t* sdone = gdone + NS;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(cdone + i, NCW);
+      mbar_init(gdone + i, GRAM ? Geo::NGW : NCW);
+      mbar_init(sdone + i, 1);
+    }
+    mbar_fence_init();
+  }
+  // coefficient matrix, column groups interleaved: element (k, j) at (k*JC + j%JC)*NSPLIT + j/JC
+  for (int e = tid; e < N * N; e += Geo::NT) {
+    const int k = e % N, j = e / N;
+    sM[(k * JC + (j % JC)) * NSPLIT + j / JC] = M[e];
+  }
+  __syncthreads();
+
+  const long long ntiles = (V + TS - 1) / TS;
+  const int nmine = static_cast<int>(blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  auto tile_pair0 = [&](int i) {  // first site pair of this CTA's i-th tile
+    return static_cast<int>((static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * (TS / 2));
+  };
+  constexpr uint32_t TILE_BYTES = TILE * sizeof(cd);
+
+  if (warp == Geo::WARP_LOAD) {
+    if (lane != 0) return;
+    for (int i = 0; i < nmine; ++i) {
+      const int st = i % NS;
+      if (i >= NS) {  // stage free: Gram and store of the tile that used it are done
+        const uint32_t par = static_cast<uint32_t>((i / NS - 1) & 1);
+        mbar_wait(gdone + st, par);
+        mbar_wait(sdone + st, par);
+      }
+      mbar_arrive_expect_tx(full + st, 2 * TILE_BYTES);
+      tma_load_2d(sbuf + st * STAGE, &tmT, 0, tile_pair0(i), full + st);
+      tma_load_2d(sbuf + st * STAGE + TILE, &tmQ, 0, tile_pair0(i), full + st);
+    }
+    return;
+  }
+
+  if (warp == Geo::WARP_STORE) {
+    if (lane != 0) return;
+    for (int i = 0; i < nmine; ++i) {
+      const int st = i % NS;
+      mbar_wait(cdone + st, static_cast<uint32_t>((i / NS) & 1));
+      tma_store_2d(&tmQ, 0, tile_pair0(i), sbuf + st * STAGE + TILE);
+      bulk_commit();
+      bulk_wait_read0();
+      mbar_arrive(sdone + st);
+    }
+    bulk_wait0();
+    return;
+  }
+
+  if (warp >= NCW) {
+    // ===================== Gram warps =====================
+    if (!GRAM) return;
+    // row = (colour c, site-in-pair sp, pair m), m fastest across lanes: 8 consecutive pairs start
+    // on 8 different 16-byte bank groups
+    auto gram_loop = [&](auto& part) {
+      part.init();
+      for (int i = 0; i < nmine; ++i) {
+        const int st = i % NS;
+        mbar_wait(cdone + st, static_cast<uint32_t>((i / NS) & 1));
+        const cd* tQ = sbuf + st * STAGE + TILE;
+        const long long site0 = 2LL * tile_pair0(i);
+#pragma unroll
+        for (int it = 0; it < (Geo::ROWS + 31) / 32; ++it) {
+          const int rr = lane + 32 * it;
+          const int m = rr % (TS / 2), sp = (rr / (TS / 2)) % 2, c = rr / TS;
+          if (rr < Geo::ROWS && site0 + 2 * m + sp < V) {
+            const cd* row = tQ + m * PAIR + sp * SITE + c;
+            part.row(row, row);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gdone + st);
+      }
+      part.store(gpart + static_cast<size_t>(blockIdx.x) * N * N);
+    };
+    switch (warp - NCW) {
+      case 0: { GramPart<N, 0> part; gram_loop(part); break; }
+      case 1: { GramPart<N, 1> part; gram_loop(part); break; }
+      case 2: { GramPart<N, 2> part; gram_loop(part); break; }
+      default: { GramPart<N, 3> part; gram_loop(part); break; }
+    }
+    return;
+  }
+
+  // ===================== update warps =====================
+  const int h = lane % NSPLIT;
+  const int lsite = warp * SPW + lane / NSPLIT;
+  const int sbase = (lsite >> 1) * PAIR + (lsite & 1) * SITE;
+  for (int i = 0; i < nmine; ++i) {
+    const int st = i % NS;
+    mbar_wait(full + st, static_cast<uint32_t>((i / NS) & 1));
+    const cd* sT = sbuf + st * STAGE + sbase;
+    cd* sQ = sbuf + st * STAGE + TILE + sbase;
+    cd acc[3][JC];
+#pragma unroll
+    for (int j = 0; j < JC; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c][j] = sQ[3 * (h * JC + j) + c];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const cd p0 = sT[3 * k], p1 = sT[3 * k + 1], p2 = sT[3 * k + 2];
+#pragma unroll
+      for (int j = 0; j < JC; ++j) {
+        const cd m = lds_cd(sM + (k * JC + j) * NSPLIT + h);
+        cmac(acc[0][j], p0, m);
+        cmac(acc[1][j], p1, m);
+        cmac(acc[2][j], p2, m);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < JC; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sQ[3 * (h * JC + j) + c] = acc[c][j];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(cdone + st);
+      if (!GRAM) mbar_arrive(gdone + st);
+    }
+  }
+}
+
+}  // namespace bcg

@@ -938,6 +938,14 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
       case 10:
         KL(c->ops->dirac_v1(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, nullptr, nullptr, c->sms, l));
         break;
+      case 11:  // first-generation Q += T*M with fused Gram
+        KL(c->ops->axpy_gram_v1(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, c->gpart, nullptr,
+                                c->sms, l));
+        break;
+      case 12:
+        KL(c->ops->axpy_gram_v1(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, nullptr, nullptr,
+                                c->sms, l));
+        break;
       case 2:
         KL(c->ops->gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), c->V, c->gpart, nullptr, c->sms, l));
         break;

@@ -25,8 +25,6 @@
 // Hand-off is by mbarriers only (inb: TMA -> stencil, ofull: stencil -> Gram + storer,
 // gdone: Gram -> loader + stencil, sdone: storer -> stencil); no __syncthreads in the loop.
 #pragma once
-#include <cuda.h>
-
 #include "common.cuh"
 #include "field_kernels.cuh"
 
@@ -84,21 +82,6 @@ struct GramPart {
       }
   }
 };
-
-// ---- tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) ----------------------------
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* smem_src) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
-               "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
-               : "memory");
-}
 
 template <int N, int G, int K, int W>
 struct ChainGeom {

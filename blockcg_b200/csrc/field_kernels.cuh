@@ -640,15 +640,23 @@ struct ShiftGeom {
   static_assert(TS % 2 == 0, "tile holds whole site pairs");
   static constexpr int PAIR = 2 * SITE + (((2 * SITE) % 2 == 0) ? 1 : 0);
   static constexpr int TILE = (TS / 2) * PAIR;  // complex per staged field tile
-  static constexpr int STAGE_ELEMS = 2 * TILE + 2 * N * N;
+  // tensor-map copies need 128-byte aligned destinations: stages are whole multiples of 8 complex
+  static constexpr int STAGE_ELEMS = (2 * TILE + 2 * N * N + 7) / 8 * 8;
   static constexpr int NSTAGE = 2;
   static constexpr size_t SMEM_BYTES = sizeof(cd) * NSTAGE * STAGE_ELEMS + 64;
   static constexpr int MAXREG = (2 * SMEM_BYTES <= 220 * 1024) ? 128 : 232;
 };
 
+// tensor maps of the fields one multishift launch touches (kernel parameter, __grid_constant__)
+struct ShiftMaps {
+  CUtensorMap Q;
+  CUtensorMap P[kMaxShifts];
+  CUtensorMap X[kMaxShifts];
+};
+
 template <int N, int TS>
 __global__ void __maxnreg__((ShiftGeom<N, TS>::MAXREG))
-shift_pipe_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rrecip,
+shift_pipe_kernel(const __grid_constant__ ShiftMaps maps, const cd* __restrict__ Rrecip,
                   const cd* __restrict__ Amats, const cd* __restrict__ Bmats, long long V, int do_backsub,
                   int n_active_fixed, const Ctrl* __restrict__ ctrl) {
   using Geo = ShiftGeom<N, TS>;
@@ -675,69 +683,56 @@ shift_pipe_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rreci
 
   const long long ntiles = (V + TS - 1) / TS;
   constexpr uint32_t MAT_BYTES = N * N * sizeof(cd);
-  constexpr uint32_t SITE_BYTES = SITE * sizeof(cd);
+  constexpr uint32_t TILE_BYTES = TILE * sizeof(cd);
 
   if (warp == NCW) {
-    // ===================== producer warp: lane l moves sites l, l+32, ... =====================
+    // ===================== producer: one lane, tensor copies of whole padded tiles =====================
+    // A field tile is a box of TS/2 site pairs, one complex wider than a pair, of the
+    // [pair][2 * 3N] view of the field: pairs land PAIR apart in shared memory, the surplus
+    // element is out of bounds (zero on load, not written on store), rows past the end of the
+    // field likewise.
+    if (lane != 0) return;
     long long it = 0;
-    long long rx0_a = 0, rx0_b = 0;  // descriptors of the two items in flight
-    int rns_a = 0, rns_b = 0, rs_a = 0, rs_b = 0;
+    int rp_a = 0, rp_b = 0, rs_a = 0, rs_b = 0;  // descriptors of the two items in flight
     auto store_item = [&](int st) {
       const cd* buf = sbuf + st * STAGE;
-      const int ns = st ? rns_b : rns_a;
-      const long long x0 = st ? rx0_b : rx0_a;
-      const int s = st ? rs_b : rs_a;
-      for (int lp = lane; 2 * lp < ns; lp += 32) {  // lane lp moves site pair lp (last one may be single)
-        const long long off = (x0 + 2 * lp) * SITE;
-        const uint32_t bytes = (2 * lp + 1 < ns) ? 2 * SITE_BYTES : SITE_BYTES;
-        if (s < 0) {
-          if (backsub) bulk_s2g(Q + off, buf + lp * PAIR, bytes);
-        } else {
-          bulk_s2g(fp.P[s] + off, buf + lp * PAIR, bytes);
-          bulk_s2g(fp.X[s] + off, buf + TILE + lp * PAIR, bytes);
-        }
+      const int s = st ? rs_b : rs_a, pr = st ? rp_b : rp_a;
+      if (s < 0) {
+        if (backsub) tma_store_2d(&maps.Q, 0, pr, buf);
+      } else {
+        tma_store_2d(&maps.P[s], 0, pr, buf);
+        tma_store_2d(&maps.X[s], 0, pr, buf + TILE);
       }
       bulk_commit();
     };
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const long long x0 = tile * TS;
-      const int ns = static_cast<int>(min(static_cast<long long>(TS), V - x0));
+      const int pair0 = static_cast<int>(tile * (TS / 2));
       for (int s = -1; s < n_active; ++s, ++it) {
         const int st = static_cast<int>(it & 1);
         const uint32_t use = static_cast<uint32_t>(it >> 1);
         if (it >= 2) {
           mbar_wait(computed + st, (use - 1) & 1u);  // item it-2 has been computed in place
           store_item(st);
-          bulk_wait_read0();  // this lane's stores have drained the buffer
-          __syncwarp();
+          bulk_wait_read0();  // the stores have drained the buffer
         }
         if (st) {
-          rx0_b = x0; rns_b = ns; rs_b = s;
+          rp_b = pair0;
+          rs_b = s;
         } else {
-          rx0_a = x0; rns_a = ns; rs_a = s;
+          rp_a = pair0;
+          rs_a = s;
         }
         cd* buf = sbuf + st * STAGE;
-        if (lane == 0) {
-          const uint32_t fld = static_cast<uint32_t>(ns) * SITE_BYTES;
-          if (s < 0) {
-            mbar_arrive_expect_tx(full + st, fld + (backsub ? MAT_BYTES : 0u));
-            if (backsub) bulk_g2s(buf + 2 * TILE, Rrecip, MAT_BYTES, full + st);
-          } else {
-            mbar_arrive_expect_tx(full + st, 2 * fld + 2 * MAT_BYTES);
-            bulk_g2s(buf + 2 * TILE, Amats + static_cast<size_t>(s) * N * N, MAT_BYTES, full + st);
-            bulk_g2s(buf + 2 * TILE + N * N, Bmats + static_cast<size_t>(s) * N * N, MAT_BYTES, full + st);
-          }
-        }
-        __syncwarp();  // expect_tx is registered before any lane's copy can complete
-        for (int lp = lane; 2 * lp < ns; lp += 32) {
-          const long long off = (x0 + 2 * lp) * SITE;
-          const uint32_t bytes = (2 * lp + 1 < ns) ? 2 * SITE_BYTES : SITE_BYTES;
-          if (s < 0) {
-            bulk_g2s(buf + lp * PAIR, Q + off, bytes, full + st);
-          } else {
-            bulk_g2s(buf + lp * PAIR, fp.P[s] + off, bytes, full + st);
-            bulk_g2s(buf + TILE + lp * PAIR, fp.X[s] + off, bytes, full + st);
-          }
+        if (s < 0) {
+          mbar_arrive_expect_tx(full + st, TILE_BYTES + (backsub ? MAT_BYTES : 0u));
+          if (backsub) bulk_g2s(buf + 2 * TILE, Rrecip, MAT_BYTES, full + st);
+          tma_load_2d(buf, &maps.Q, 0, pair0, full + st);
+        } else {
+          mbar_arrive_expect_tx(full + st, 2 * TILE_BYTES + 2 * MAT_BYTES);
+          bulk_g2s(buf + 2 * TILE, Amats + static_cast<size_t>(s) * N * N, MAT_BYTES, full + st);
+          bulk_g2s(buf + 2 * TILE + N * N, Bmats + static_cast<size_t>(s) * N * N, MAT_BYTES, full + st);
+          tma_load_2d(buf, &maps.P[s], 0, pair0, full + st);
+          tma_load_2d(buf + TILE, &maps.X[s], 0, pair0, full + st);
         }
       }
     }

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "field_kernels.cuh"
 #include "dirac_chain.cuh"
+#include "axpy_pipe.cuh"
 
 namespace bcg {
 
@@ -22,6 +23,8 @@ struct OpsTable {
               int* launches);
   int (*axpy_gram)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
                    const Ctrl* ctrl, int sms, int* launches);
+  int (*axpy_gram_v1)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
+                      const Ctrl* ctrl, int sms, int* launches);
   int (*rescale_add)(cudaStream_t st, cd* dst, const cd* L, const cd* src, double r, long long V, int sms,
                      int* launches);
   int (*trsm)(cudaStream_t st, cd* Q, const cd* R, long long V, const Ctrl* ctrl, int sms, int* launches);
@@ -76,6 +79,21 @@ inline int make_chain_map(CUtensorMap* m, const cd* base, int win, int win_strid
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(cudaErrorInvalidValue);
 }
 
+// 2-D view [site pair][2 * site complex] of a field; box = `rows` pairs of `box` complex each
+// (box > 2 * site pads every pair in shared memory, see make_chain_map)
+inline int make_pair_map(CUtensorMap* m, const cd* base, int site, int box, long long npairs, int rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return -static_cast<int>(cudaErrorNotSupported);
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(4 * site), static_cast<cuuint64_t>(npairs)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(2 * site) * sizeof(cd)};
+  const cuuint32_t bx[2] = {static_cast<cuuint32_t>(2 * box), static_cast<cuuint32_t>(rows)};
+  const cuuint32_t es[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<cd*>(base), dims, strides, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(cudaErrorInvalidValue);
+}
+
 #ifdef BCG_N  // ---- per-N implementation, included only by inst.cu ----------------------------
 
 constexpr int kNT = 192;  // 6 warps: one 4x4 Gram block per warp at N = 12, whole sites per CTA
@@ -110,6 +128,9 @@ struct Ops {
   static constexpr int SHIFT_TS = 32;  // sites per pipeline tile
   using SG = ShiftGeom<N, SHIFT_TS>;
   static constexpr bool PIPE_OK = SG::SMEM_BYTES <= 227 * 1024;
+  static constexpr bool APIPE = (N % 2 == 0 && N >= 4);  // pipelined Q += T*M (axpy_pipe.cuh)
+  static constexpr int APIPE_TS = 32;
+  using APG = AxpyPipeGeom<APIPE ? N : 4, APIPE_TS>;
   static constexpr bool CHAIN = Tune<N>::CHAIN_G > 0;
   static constexpr int CG_ = CHAIN ? Tune<N>::CHAIN_G : 1, CK = Tune<N>::CHAIN_K, CW = Tune<N>::CHAIN_W;
   using CGm = ChainGeom<N, CG_, CHAIN ? CK : 16 / CG_, CW>;
@@ -137,6 +158,12 @@ struct Ops {
     c.trsm = occupancy_blocks(trsm_kernel<N, kNT>, kNT, 0, sms);
     c.shift = occupancy_blocks(shift_update_kernel<N, kNT>, kNT, SHIFT_SMEM, sms);
     if constexpr (PIPE_OK) c.pipe = occupancy_blocks(shift_pipe_kernel<N, SHIFT_TS>, SG::NT, SG::SMEM_BYTES, sms);
+    if constexpr (APIPE) {
+      cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)APG::SMEM_BYTES);
+      cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)APG::SMEM_BYTES);
+    }
     if constexpr (CHAIN) {
       cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)CGm::SMEM_BYTES);
@@ -235,6 +262,26 @@ struct Ops {
 
   static int axpy_gram(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
                        const Ctrl* ctrl, int sms, int* launches) {
+    if constexpr (APIPE) {
+      prepare(sms);
+      alignas(64) CUtensorMap tmQ, tmT;
+      int e = make_pair_map(&tmQ, Q, 3 * N, APG::PAIR, (V + 1) / 2, APIPE_TS / 2);
+      if (!e) e = make_pair_map(&tmT, T, 3 * N, APG::PAIR, (V + 1) / 2, APIPE_TS / 2);
+      if (e) return e;
+      const int grid = clamp_grid((V + APIPE_TS - 1) / APIPE_TS, sms);
+      if (gpart != nullptr)
+        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, gpart, ctrl);
+      else
+        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, nullptr, ctrl);
+      if (launches) ++*launches;
+      e = err();
+      return e ? e : (gpart != nullptr ? grid : 0);
+    }
+    return axpy_gram_v1(st, Q, T, M, V, gpart, ctrl, sms, launches);
+  }
+
+  static int axpy_gram_v1(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
+                          const Ctrl* ctrl, int sms, int* launches) {
     prepare(sms);
     const long long ntiles = (3 * V + kNT - 1) / kNT;
     if (gpart != nullptr) {
@@ -276,7 +323,21 @@ struct Ops {
     prepare(sms);
     if constexpr (PIPE_OK) {
       const int grid = clamp_grid((V + SHIFT_TS - 1) / SHIFT_TS, caps().pipe);
-      shift_pipe_kernel<N, SHIFT_TS><<<grid, SG::NT, SG::SMEM_BYTES, st>>>(Q, *fp, Rm, A, B, V, do_backsub,
+      // tensor maps of every field the launch may touch (n_active is only known on the device)
+      alignas(64) ShiftMaps maps;
+      const long long npairs = (V + 1) / 2;
+      int e = make_pair_map(&maps.Q, Q, 3 * N, SG::PAIR, npairs, SHIFT_TS / 2);
+      for (int s = 0; s < kMaxShifts && !e; ++s) {
+        if (fp->P[s] == nullptr || fp->X[s] == nullptr) {
+          maps.P[s] = maps.Q;  // never used: the device loop stops at n_active
+          maps.X[s] = maps.Q;
+          continue;
+        }
+        e = make_pair_map(&maps.P[s], fp->P[s], 3 * N, SG::PAIR, npairs, SHIFT_TS / 2);
+        if (!e) e = make_pair_map(&maps.X[s], fp->X[s], 3 * N, SG::PAIR, npairs, SHIFT_TS / 2);
+      }
+      if (e) return e;
+      shift_pipe_kernel<N, SHIFT_TS><<<grid, SG::NT, SG::SMEM_BYTES, st>>>(maps, Rm, A, B, V, do_backsub,
                                                                            n_active_fixed, ctrl);
       if (launches) ++*launches;
       return err();
@@ -307,6 +368,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::dirac_v1,
                              &Ops<N>::gram,
                              &Ops<N>::axpy_gram,
+                             &Ops<N>::axpy_gram_v1,
                              &Ops<N>::rescale_add,
                              &Ops<N>::trsm,
                              &Ops<N>::shift_update,

@@ -139,7 +139,7 @@ int bcg_solve_sbcgrq(bcg_ctx* ctx, double* const* x_host, const double* b_host, 
  * 2 Gram, 3 Q -= T*alpha with fused Gram, 4 multishift update over n_shifts shifts (7: its
  * first-generation register-direct variant),
  * 5 X += P*M, 6 P = P*L + Q, 9 / 10: the first-generation stencil with / without the fused
- * Gram (kept for comparison).  Fields are the context's own scratch, filled by the caller
+ * Gram, 11 / 12: the first-generation Q += T*M with / without it (kept for comparison).  Fields are the context's own scratch, filled by the caller
  * through handles f0..f3 where needed. */
 int bcg_bench_kernel(bcg_ctx* ctx, int which, int reps, int n_shifts, const int* handles, int n_handles,
                      double* ms_out, int64_t* launches_out);

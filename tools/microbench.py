@@ -36,6 +36,8 @@ def run(V, N, S, reps, seed=0):
             ("gram", 2, hs[:2], 1, 2 * F),
             ("axpy_gram", 3, hs[:2], 1, 3 * F),
             ("axpy", 5, hs[:2], 1, 3 * F),
+            ("axpy_gram_v1", 11, hs[:2], 1, 3 * F),
+            ("axpy_v1", 12, hs[:2], 1, 3 * F),
             ("rescale_add", 6, hs[:2], 1, 3 * F),
             ("shift_update_S%d" % S, 4, hs[:1 + 2 * S], S, (2 + 4 * S) * F),
             ("shift_update_S1", 4, hs[:3], 1, 6 * F),
