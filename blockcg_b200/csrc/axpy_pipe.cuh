@@ -124,7 +124,9 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_wait(cdone + st, static_cast<uint32_t>((i / NS) & 1));
         const cd* tQ = sbuf + st * STAGE + TILE;
         const long long site0 = 2LL * tile_pair0(i);
-#pragma unroll
+        // not unrolled: four different Gram loops plus the stencil loop must stay resident in the
+        // instruction cache together (stall_no_instruction tripled when they did not)
+#pragma unroll 1
         for (int it = 0; it < (Geo::ROWS + 31) / 32; ++it) {
           const int rr = lane + 32 * it;
           const int m = rr % (TS / 2), sp = (rr / (TS / 2)) % 2, c = rr / TS;
@@ -136,7 +138,9 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(gdone + st);
       }
-      part.store(gpart + static_cast<size_t>(blockIdx.x) * N * N);
+      // scratch: the T tile of stage (warp - NCW); every update has finished with it by now
+      part.store(gpart + (static_cast<size_t>(kGramRawOff) + blockIdx.x) * N * N, sbuf + (warp - NCW) * STAGE);
+      gram_group_reduce<N>(gpart, warp - NCW);
     };
     switch (warp - NCW) {
       case 0: { GramPart<N, 0> part; gram_loop(part); break; }

@@ -229,7 +229,7 @@ int gram_finalize(bcg_ctx* c, int nparts, const cd** src, int* nsrc, int* launch
   }
   if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
   const size_t nn = c->L.nn();
-  gram_reduce_kernel<<<1, kSmallThreads, nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, nparts, c->N);
+  gram_reduce_kernel<<<1, kSmallThreads, (1 + kRedSlices) * nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, nparts, c->N);
   if (launches) ++*launches;
   CU(cudaGetLastError());
   NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
@@ -243,7 +243,7 @@ int gram_to_gred(bcg_ctx* c, const cd* a, const cd* b, int* launches) {
   int np = c->ops->gram(c->stream, a, b, c->V, c->gpart, nullptr, c->sms, launches);
   KL(np);
   const size_t nn = c->L.nn();
-  gram_reduce_kernel<<<1, kSmallThreads, nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
+  gram_reduce_kernel<<<1, kSmallThreads, (1 + kRedSlices) * nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
   if (launches) ++*launches;
   CU(cudaGetLastError());
   if (c->nranks > 1) {
@@ -329,6 +329,7 @@ int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, in
   c->L.S = max_shifts;
   c->gpart_elems = static_cast<size_t>(c->ops->max_partials(c->sms)) * c->L.nn();
   CU(cudaMalloc(&c->gpart, c->gpart_elems * sizeof(cd)));
+  CU(cudaMemset(c->gpart, 0, c->gpart_elems * sizeof(cd)));  // arrival counters of gram_group_reduce start at zero
   CU(cudaMalloc(&c->gred, c->L.nn() * sizeof(cd)));
   CU(cudaMalloc(&c->mats, c->L.total() * sizeof(cd)));
   CU(cudaMemset(c->mats, 0, c->L.total() * sizeof(cd)));
@@ -467,7 +468,7 @@ int bcg_op(bcg_ctx* c, int out, int in, double sigma, double* gram_host) {
   KL(np);
   if (gram_host) {
     const size_t nn = c->L.nn();
-    gram_reduce_kernel<<<1, kSmallThreads, nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
+    gram_reduce_kernel<<<1, kSmallThreads, (1 + kRedSlices) * nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
     CU(cudaGetLastError());
     if (c->nranks > 1) NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
     CU(cudaMemcpyAsync(gram_host, c->gred, nn * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));

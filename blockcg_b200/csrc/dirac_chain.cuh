@@ -65,23 +65,95 @@ struct GramPart {
       for (int j = 0; j < NC; ++j)
         if (!LOWER || j <= i) cmac_conj(acc[i][j], a[i], b[j]);
   }
-  // xor-tree over the lanes (fixed order), lane 0 writes its entries of the N x N column-major block
-  __device__ __forceinline__ void store(cd* __restrict__ dstNN) {
+  // Cross-lane sum and store of the finished accumulators.  Code that runs once per launch is
+  // paid for in instruction-cache misses (~40 cycles per cold instruction), so nothing here is
+  // unrolled beyond the register-to-shared spill: every lane parks its NENT accumulators in
+  // `scratch` ([entry][lane], NENT * 32 complex, private to this warp), then lane t adds up the
+  // 32 values of entry t in lane order (fixed => deterministic) and writes it into the N x N
+  // column-major block.
+  static constexpr int NENT = LOWER ? NC * (NC + 1) / 2 : NR * NC;
+  __device__ __forceinline__ void store(cd* __restrict__ dstNN, cd* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31;
+    int idx = 0;
 #pragma unroll
     for (int i = 0; i < NR; ++i)
 #pragma unroll
       for (int j = 0; j < NC; ++j) {
         if (LOWER && j > i) continue;
-        double re = acc[i][j].x, im = acc[i][j].y;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          re += __shfl_xor_sync(0xffffffffu, re, off);
-          im += __shfl_xor_sync(0xffffffffu, im, off);
-        }
-        if ((threadIdx.x & 31) == 0) dstNN[(R0 + i) + N * (C0 + j)] = cmake(re, im);
+        scratch[idx * 32 + lane] = acc[i][j];
+        ++idx;
       }
+    __syncwarp();
+#pragma unroll 1
+    for (int t = lane; t < NENT; t += 32) {
+      int i = 0, j = t;  // entry t in the enumeration order above
+      if (LOWER) {
+        while (j > i) {
+          j -= i + 1;
+          ++i;
+        }
+      } else {
+        i = t / NC;
+        j = t - i * NC;
+      }
+      double re = 0.0, im = 0.0;
+#pragma unroll 4
+      for (int l = 0; l < 32; ++l) {
+        const cd v = scratch[t * 32 + l];
+        re += v.x;
+        im += v.y;
+      }
+      dstNN[(R0 + i) + N * (C0 + j)] = cmake(re, im);
+    }
   }
 };
+
+// ---- second level of the Gram reduction, inside the producing kernel ---------------------------
+// The per-CTA partial blocks are not handed to the coefficient kernel one by one (a single CTA
+// pulling ~150 blocks out of L2 is a 5-10 us latency chain in every iteration): CTAs form groups
+// of kGramGroup consecutive blockIdx, and the group member that finishes LAST adds the group's
+// blocks, in blockIdx order, into one block.  Which member is last varies from run to run, what
+// it computes does not => still bit-reproducible, no floating-point atomics.
+// Buffer layout (complex units of N*N): [0, ngroups) group sums | [kGramRawOff, +grid) raw partial
+// blocks | [kGramCntOff] arrival counters (unsigned, zero at rest: the last member resets its own).
+constexpr int kGramGroup = 8;
+constexpr int kGramRawOff = 1024;
+constexpr int kGramCntOff = 3072;
+// Called by the 4 Gram warps (128 threads, named barrier 1) after each has stored its part of the
+// raw block.
+template <int N>
+__device__ __noinline__ void gram_group_reduce(cd* __restrict__ gbuf, int gram_warp) {
+  constexpr int nn = N * N;
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (gram_warp != 0) return;
+  const int lane = threadIdx.x & 31;
+  const int group = blockIdx.x / kGramGroup;
+  const int first = group * kGramGroup;
+  const int members = min(kGramGroup, static_cast<int>(gridDim.x) - first);
+  unsigned* cnt = reinterpret_cast<unsigned*>(gbuf + static_cast<size_t>(kGramCntOff) * nn) + group;
+  unsigned old = 0;
+  if (lane == 0) old = atomicAdd(cnt, 1u);
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old != static_cast<unsigned>(members - 1)) return;
+  __threadfence();
+  const cd* raw = gbuf + (static_cast<size_t>(kGramRawOff) + first) * nn;
+  cd* dst = gbuf + static_cast<size_t>(group) * nn;
+#pragma unroll 1
+  for (int e = lane; e < nn; e += 32) {
+    const int i = e % N, j = e / N;
+    if (i < j) continue;  // only the lower triangle is produced and consumed
+    cd v[kGramGroup];
+#pragma unroll
+    for (int m = 0; m < kGramGroup; ++m)
+      v[m] = (m < members) ? __ldcg(reinterpret_cast<const double2*>(raw + static_cast<size_t>(m) * nn + e)) : czero();
+    cd sum = v[0];
+#pragma unroll
+    for (int m = 1; m < kGramGroup; ++m) sum = cadd(sum, v[m]);  // absent members contribute +0
+    dst[e] = sum;
+  }
+  if (lane == 0) *cnt = 0u;
+}
 
 template <int N, int G, int K, int W>
 struct ChainGeom {
@@ -200,7 +272,9 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         mbar_wait(ofull + (t & 1), static_cast<uint32_t>((t >> 1) & 1));
         const cd* tP = sP + (t % SP) * (K * PP);  // P-load t holds P at this tile's out sites
         const cd* tO = sO + (t % SO) * (K * PP);
-#pragma unroll
+        // not unrolled: four different Gram loops plus the stencil loop must stay resident in the
+        // instruction cache together (stall_no_instruction tripled when they did not)
+#pragma unroll 1
         for (int it = 0; it < (Geo::ROWS + 31) / 32; ++it) {
           const int rr = lane + 32 * it;
           const int k = rr % K, s = (rr / K) % W, c = rr / (K * W);
@@ -213,7 +287,10 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(gdone + (t & 3));
       }
-      part.store(gpart + static_cast<size_t>(blockIdx.x) * N * N);
+      // scratch: a P ring slot the last tile does not use (slot (T-1) % SP is still being read)
+      part.store(gpart + (static_cast<size_t>(kGramRawOff) + blockIdx.x) * N * N,
+                 sP + ((T + (warp - Geo::NSW)) % SP) * (K * PP));
+      gram_group_reduce<N>(gpart, warp - Geo::NSW);
     };
     switch (warp - Geo::NSW) {
       case 0: { GramPart<N, 0> part; gram_loop(part); break; }

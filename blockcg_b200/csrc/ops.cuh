@@ -233,7 +233,7 @@ struct Ops {
             tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl);
       if (launches) ++*launches;
       e = err();
-      return e ? e : (gpart != nullptr ? pl.grid : 0);
+      return e ? e : (gpart != nullptr ? (pl.grid + kGramGroup - 1) / kGramGroup : 0);
     }
     return dirac_v1(st, in, out, U, V, m2, sigma, gpart, ctrl, sms, launches);
   }
@@ -275,7 +275,7 @@ struct Ops {
         axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, nullptr, ctrl);
       if (launches) ++*launches;
       e = err();
-      return e ? e : (gpart != nullptr ? grid : 0);
+      return e ? e : (gpart != nullptr ? (grid + kGramGroup - 1) / kGramGroup : 0);
     }
     return axpy_gram_v1(st, Q, T, M, V, gpart, ctrl, sms, launches);
   }
@@ -355,7 +355,8 @@ struct Ops {
     return err();
   }
 
-  static int max_partials(int sms) { return 32 * sms; }
+  // see gram_group_reduce() for the layout of the partial-Gram buffer
+  static int max_partials(int sms) { return (32 * sms > kGramCntOff + 8) ? 32 * sms : kGramCntOff + 8; }
 };
 
 template <int N>

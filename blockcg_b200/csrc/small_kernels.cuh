@@ -10,7 +10,7 @@
 
 namespace bcg {
 
-constexpr int kSmallThreads = 256;
+constexpr int kSmallThreads = 512;
 constexpr double kEps = 2.220446049250313e-16;
 
 // Device-memory block of coefficient matrices (offsets in units of N*N complex).
@@ -40,44 +40,58 @@ struct MatLayout {
   __host__ __device__ size_t total() const { return (M_FIXED_COUNT + 4 * S) * nn(); }
 };
 
+// (row, column) of every linear matrix index, filled once per kernel: an integer division by
+// the run-time N costs more than a whole complex multiply-add chain of these little kernels.
+__shared__ int g_ij[1024];  // i | j << 16
+__device__ __forceinline__ void sm_init_ij(int N) {
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) g_ij[e] = (e % N) | ((e / N) << 16);
+  __syncthreads();
+}
+#define BCG_IJ(e, i, j) const int ij_##i = g_ij[e]; const int i = ij_##i & 0xffff, j = ij_##i >> 16
+
 // ---- CTA-wide primitives; every function ends with __syncthreads() -------------------
-__device__ __forceinline__ void sm_copy(cd* dst, const cd* src, int n) {
+__device__ __noinline__ void sm_copy(cd* dst, const cd* src, int n) {
   for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = src[e];
   __syncthreads();
 }
-__device__ __forceinline__ void sm_identity(cd* dst, int N) {
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) dst[e] = cmake((e % N) == (e / N) ? 1.0 : 0.0, 0.0);
+__device__ __noinline__ void sm_identity(cd* dst, int N) {
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    BCG_IJ(e, i, j);
+    dst[e] = cmake(i == j ? 1.0 : 0.0, 0.0);
+  }
   __syncthreads();
 }
 // C = A*B ; C must not alias A or B
-__device__ __forceinline__ void sm_mm(cd* C, const cd* A, const cd* B, int N) {
+__device__ __noinline__ void sm_mm(cd* C, const cd* A, const cd* B, int N) {
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int i = e % N, j = e / N;
+    BCG_IJ(e, i, j);
     cd s = czero();
+#pragma unroll 4
     for (int k = 0; k < N; ++k) cmac(s, A[i + N * k], B[k + N * j]);
     C[e] = s;
   }
   __syncthreads();
 }
 // C = A * B^dag
-__device__ __forceinline__ void sm_mm_adj(cd* C, const cd* A, const cd* B, int N) {
+__device__ __noinline__ void sm_mm_adj(cd* C, const cd* A, const cd* B, int N) {
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int i = e % N, j = e / N;
+    BCG_IJ(e, i, j);
     cd s = czero();
+#pragma unroll 4
     for (int k = 0; k < N; ++k) cmac(s, A[i + N * k], cconj(B[j + N * k]));
     C[e] = s;
   }
   __syncthreads();
 }
-__device__ __forceinline__ void sm_adjoint(cd* C, const cd* A, int N) {
+__device__ __noinline__ void sm_adjoint(cd* C, const cd* A, int N) {
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int i = e % N, j = e / N;
+    BCG_IJ(e, i, j);
     C[e] = cconj(A[j + N * i]);
   }
   __syncthreads();
 }
 // out[i] = || row i of A ||_2   (delta.rowwise().norm())
-__device__ __forceinline__ void sm_rownorms(double* out, const cd* A, int N) {
+__device__ __noinline__ void sm_rownorms(double* out, const cd* A, int N) {
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     double s = 0.0;
     for (int j = 0; j < N; ++j) s += cabs2(A[i + N * j]);
@@ -86,35 +100,67 @@ __device__ __forceinline__ void sm_rownorms(double* out, const cd* A, int N) {
   __syncthreads();
 }
 
-// Deterministic reduction of the per-CTA partial Grams (fixed order over p),
-// lower triangle + diagonal only, upper = conjugate mirror (fields.hpp:103-122).
-__device__ __forceinline__ void sm_reduce_gram(cd* G, const cd* __restrict__ gpart, int nparts, int N) {
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int i = e % N, j = e / N;
-    if (i >= j) {
-      double re = 0.0, im = 0.0;
-      int p = 0;
-      for (; p + 4 <= nparts; p += 4) {  // 4 loads in flight, summed in index order
-        const cd a = gpart[static_cast<size_t>(p) * N * N + e];
-        const cd b = gpart[static_cast<size_t>(p + 1) * N * N + e];
-        const cd c = gpart[static_cast<size_t>(p + 2) * N * N + e];
-        const cd d = gpart[static_cast<size_t>(p + 3) * N * N + e];
-        re += a.x; im += a.y;
-        re += b.x; im += b.y;
-        re += c.x; im += c.y;
-        re += d.x; im += d.y;
-      }
-      for (; p < nparts; ++p) {
-        const cd a = gpart[static_cast<size_t>(p) * N * N + e];
-        re += a.x; im += a.y;
-      }
-      G[e] = cmake(re, im);
+// Deterministic reduction of the per-CTA partial Grams, lower triangle + diagonal only, upper =
+// conjugate mirror (fields.hpp:103-122).  The loop over partials is latency-bound (one L2 round
+// trip per load), so every lower-triangle entry is summed by NSL = min(kRedSlices, blockDim/E)
+// threads, thread q taking partials q, q+NSL, ... in index order with 16 loads in flight, and the
+// slice sums are then combined in slice order: a fixed summation tree, identical from run to run.
+// `scratch`: kRedSlices * N*(N+1)/2 complex (may not alias G).
+constexpr int kRedSlices = 8;
+__device__ __noinline__ void sm_reduce_gram(cd* G, const cd* __restrict__ gpart, int nparts, int N,
+                                               cd* scratch) {
+  const int nn = N * N, E = N * (N + 1) / 2;
+  int nsl = static_cast<int>(blockDim.x) / E;
+  nsl = nsl < 1 ? 1 : (nsl > kRedSlices ? kRedSlices : nsl);
+  for (int w = threadIdx.x; w < E * nsl; w += blockDim.x) {
+    const int t = w % E, q = w / E;
+    int j = 0, rest = t;  // packed lower triangle, column by column: column j holds N - j entries
+    while (rest >= N - j) {
+      rest -= N - j;
+      ++j;
     }
+    const int e = (j + rest) + N * j;
+    double re = 0.0, im = 0.0;
+    int p = q;
+    for (; p + 15 * nsl < nparts; p += 16 * nsl) {
+      cd v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = gpart[static_cast<size_t>(p + u * nsl) * nn + e];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        re += v[u].x;
+        im += v[u].y;
+      }
+    }
+    for (; p + 3 * nsl < nparts; p += 4 * nsl) {
+      cd v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = gpart[static_cast<size_t>(p + u * nsl) * nn + e];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        re += v[u].x;
+        im += v[u].y;
+      }
+    }
+    for (; p < nparts; p += nsl) {
+      const cd a = gpart[static_cast<size_t>(p) * nn + e];
+      re += a.x;
+      im += a.y;
+    }
+    scratch[w] = cmake(re, im);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int i = e % N, j = e / N;
-    if (i < j) G[e] = cconj(G[j + N * i]);
+  for (int t = threadIdx.x; t < E; t += blockDim.x) {
+    int j = 0, rest = t;
+    while (rest >= N - j) {
+      rest -= N - j;
+      ++j;
+    }
+    const int i = j + rest;
+    cd sum = scratch[t];
+    for (int q = 1; q < nsl; ++q) sum = cadd(sum, scratch[q * E + t]);
+    G[i + N * j] = sum;
+    if (i != j) G[j + N * i] = cconj(sum);
   }
   __syncthreads();
 }
@@ -123,33 +169,41 @@ __device__ __forceinline__ void sm_reduce_gram(cd* G, const cd* __restrict__ gpa
 // Hermitian G, result returned as R = L^dag (upper, exactly zero below the
 // diagonal), as fields.hpp:142.  Returns -1 or the index of the first
 // non-positive pivot (uniform across the CTA).  Lw: N*N scratch.
-__device__ __forceinline__ int sm_chol_upper(cd* R, const cd* G, cd* Lw, int N, int* s_info) {
+__device__ __noinline__ int sm_chol_upper(cd* R, const cd* G, cd* Lw, int N, int* s_info) {
   sm_copy(Lw, G, N * N);
-  if (threadIdx.x == 0) *s_info = -1;
-  __syncthreads();
-  for (int k = 0; k < N; ++k) {
-    // column k below the diagonal: s_i = L(i,k) - sum_j<k L(i,j) conj(L(k,j)); pivot row i == k
-    for (int i = k + threadIdx.x; i < N; i += blockDim.x) {
-      if (i == k) {
-        double x = Lw[k + N * k].x;
-        for (int j = 0; j < k; ++j) x -= cabs2(Lw[k + N * j]);
-        if (!(x > 0.0)) *s_info = k;
-        Lw[k + N * k] = cmake(sqrt(x), 0.0);
-      } else {
-        cd s = Lw[i + N * k];
-        for (int j = 0; j < k; ++j) cmsub(s, Lw[i + N * j], cconj(Lw[k + N * j]));
-        Lw[i + N * k] = s;
+  if (threadIdx.x < 32) {  // N dependent column steps: one warp, __syncwarp between them (cf. warp_lu_solve)
+    const int lane = threadIdx.x;
+    int info = -1;
+    for (int k = 0; k < N; ++k) {
+      // column k on and below the diagonal: s_i = L(i,k) - sum_j<k L(i,j) conj(L(k,j))
+      double x = 0.0;
+      for (int i = k + lane; i < N; i += 32) {
+        if (i == k) {
+          x = Lw[k + N * k].x;
+          for (int j = 0; j < k; ++j) x -= cabs2(Lw[k + N * j]);
+          Lw[k + N * k] = cmake(sqrt(x), 0.0);
+        } else {
+          cd sacc = Lw[i + N * k];
+          for (int j = 0; j < k; ++j) cmsub(sacc, Lw[i + N * j], cconj(Lw[k + N * j]));
+          Lw[i + N * k] = sacc;
+        }
       }
+      x = __shfl_sync(0xffffffffu, x, 0);  // lane 0 owns the pivot (i == k  <=>  lane == 0)
+      __syncwarp();
+      if (!(x > 0.0)) {
+        info = k;
+        break;
+      }
+      const double d = Lw[k + N * k].x;
+      for (int i = k + 1 + lane; i < N; i += 32) Lw[i + N * k] = cscale(Lw[i + N * k], 1.0 / d);
+      __syncwarp();
     }
-    __syncthreads();
-    if (*s_info >= 0) break;
-    const double x = Lw[k + N * k].x;
-    for (int i = k + 1 + threadIdx.x; i < N; i += blockDim.x) Lw[i + N * k] = cscale(Lw[i + N * k], 1.0 / x);
-    __syncthreads();
+    if (lane == 0) *s_info = info;
   }
+  __syncthreads();
   const int info = *s_info;
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
-    const int i = e % N, j = e / N;
+    BCG_IJ(e, i, j);
     R[e] = (j >= i) ? cconj(Lw[j + N * i]) : czero();
   }
   __syncthreads();
@@ -173,27 +227,29 @@ struct LuWork {
   int* imisc;     // [0] nonzero [1] rank [2] br [3] bc
 };
 
-__device__ __forceinline__ void sm_lu_solve(cd* X, cd* lu, const LuWork& w, int N) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  if (tid == 0) {
-    w.misc[0] = 0.0;
-    w.imisc[0] = N;
-  }
-  __syncthreads();
+// The factorisation is a chain of ~10 N dependent little steps: it runs in ONE warp (the steps
+// are separated by __syncwarp, an order of magnitude cheaper than a CTA barrier) while the
+// other warps of the CTA wait at the closing __syncthreads.
+// Lanes form a 16 x 2 grid over (row, column) so that no loop needs an integer division; pivots
+// are compared by squared modulus (same order as Eigen's abs unless two candidates agree to
+// rounding), and divisions by a pivot become one reciprocal per step plus multiplications.
+__device__ __noinline__ void warp_lu_solve(cd* X, cd* lu, const LuWork& w, int N) {
+  const int lane = threadIdx.x & 31, li = lane & 15, lj = lane >> 4;
+  double maxpivot2 = 0.0;
+  int nonzero = N;
   for (int k = 0; k < N; ++k) {
     // ---- pivot search over the trailing (N-k)^2 block ----
-    const int m = N - k;
     double bv = -1.0;
     int bi = 0x7fffffff;
-    for (int e = tid; e < m * m; e += blockDim.x) {
-      const int i = k + e % m, j = k + e / m;
-      const double a = hypot(lu[i + N * j].x, lu[i + N * j].y);
-      const int lin = i + N * j;  // column-major scan order == Eigen's visitor order
-      if (a > bv || (a == bv && lin < bi)) {
-        bv = a;
-        bi = lin;
+    for (int j = k + lj; j < N; j += 2)
+      for (int i = k + li; i < N; i += 16) {
+        const double a = cabs2(lu[i + N * j]);
+        const int lin = i + N * j;  // column-major scan order == Eigen's visitor order
+        if (a > bv || (a == bv && lin < bi)) {
+          bv = a;
+          bi = lin;
+        }
       }
-    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
@@ -203,63 +259,41 @@ __device__ __forceinline__ void sm_lu_solve(cd* X, cd* lu, const LuWork& w, int 
         bi = oi;
       }
     }
-    if (lane == 0) {
-      w.red_v[warp] = bv;
-      w.red_i[warp] = bi;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double v = w.red_v[0];
-      int ix = w.red_i[0];
-      for (int ww = 1; ww < nwarp; ++ww)
-        if (w.red_v[ww] > v || (w.red_v[ww] == v && w.red_i[ww] < ix)) {
-          v = w.red_v[ww];
-          ix = w.red_i[ww];
-        }
-      if (v == 0.0) {
-        w.imisc[0] = k;  // nonzero pivots
-        w.imisc[2] = -1;
-      } else {
-        if (v > w.misc[0]) w.misc[0] = v;
-        w.imisc[2] = ix % N;
-        w.imisc[3] = ix / N;
-        w.rt[k] = ix % N;
-        w.ct[k] = ix / N;
-      }
-    }
-    __syncthreads();
-    if (w.imisc[2] < 0) {
-      for (int i = k + tid; i < N; i += blockDim.x) w.rt[i] = w.ct[i] = i;
-      __syncthreads();
+    if (bv == 0.0) {  // the whole trailing block vanishes
+      nonzero = k;
+      for (int i = k + lane; i < N; i += 32) w.rt[i] = w.ct[i] = i;
+      __syncwarp();
       break;
     }
-    const int br = w.imisc[2], bc = w.imisc[3];
+    if (bv > maxpivot2) maxpivot2 = bv;
+    const int bc = bi / N, br = bi - bc * N;
+    if (lane == 0) {
+      w.rt[k] = br;
+      w.ct[k] = bc;
+    }
     if (br != k)
-      for (int j = tid; j < N; j += blockDim.x) {
+      for (int j = lane; j < N; j += 32) {
         const cd t = lu[k + N * j];
         lu[k + N * j] = lu[br + N * j];
         lu[br + N * j] = t;
       }
-    __syncthreads();
+    __syncwarp();
     if (bc != k)
-      for (int i = tid; i < N; i += blockDim.x) {
+      for (int i = lane; i < N; i += 32) {
         const cd t = lu[i + N * k];
         lu[i + N * k] = lu[i + N * bc];
         lu[i + N * bc] = t;
       }
-    __syncthreads();
-    const cd piv = lu[k + N * k];
-    for (int i = k + 1 + tid; i < N; i += blockDim.x) lu[i + N * k] = cdiv(lu[i + N * k], piv);
-    __syncthreads();
-    const int m1 = N - k - 1;
-    for (int e = tid; e < m1 * m1; e += blockDim.x) {
-      const int i = k + 1 + e % m1, j = k + 1 + e / m1;
-      cmsub(lu[i + N * j], lu[i + N * k], lu[k + N * j]);
-    }
-    __syncthreads();
+    __syncwarp();
+    const cd rpiv = cdiv(cmake(1.0, 0.0), lu[k + N * k]);
+    for (int i = k + 1 + lane; i < N; i += 32) lu[i + N * k] = cmul(lu[i + N * k], rpiv);
+    __syncwarp();
+    for (int j = k + 1 + lj; j < N; j += 2)
+      for (int i = k + 1 + li; i < N; i += 16) cmsub(lu[i + N * j], lu[i + N * k], lu[k + N * j]);
+    __syncwarp();
   }
-  // ---- permutations and rank ----
-  if (tid == 0) {
+  // ---- permutations and rank (FullPivLU.h:317-341: pivots above eps * N * |maxpivot| count) ----
+  if (lane == 0) {
     for (int i = 0; i < N; ++i) w.p[i] = w.q[i] = i;
     for (int k = N - 1; k >= 0; --k) {
       const int t = w.p[k];
@@ -271,46 +305,129 @@ __device__ __forceinline__ void sm_lu_solve(cd* X, cd* lu, const LuWork& w, int 
       w.q[k] = w.q[w.ct[k]];
       w.q[w.ct[k]] = t;
     }
-    const double thr = w.misc[0] * (kEps * N);
-    int rank = 0;
-    for (int i = 0; i < w.imisc[0]; ++i) rank += (hypot(lu[i + N * i].x, lu[i + N * i].y) > thr);
-    w.imisc[1] = rank;
   }
-  __syncthreads();
-  const int rank = w.imisc[1];
+  const double thr = sqrt(maxpivot2) * (kEps * N);
+  int rank = 0;
+  for (int i0 = 0; i0 < nonzero; i0 += 32) {
+    const int i = i0 + lane;
+    const bool big = (i < nonzero) && (cabs2(lu[i + N * i]) > thr * thr);
+    rank += __popc(__ballot_sync(0xffffffffu, big));
+  }
+  __syncwarp();
   if (rank == 0) {
-    for (int e = tid; e < N * N; e += blockDim.x) X[e] = czero();
-    __syncthreads();
+    for (int e = lane; e < N * N; e += 32) X[e] = czero();
     return;
   }
-  // c = P * B : row p[i] of c = row i of B
-  for (int e = tid; e < N * N; e += blockDim.x) {
-    const int i = e % N, col = e / N;
-    w.c[w.p[i] + N * col] = X[i + N * col];
-  }
-  __syncthreads();
+  // c = P * B : row p[i] of c = row i of B ; reciprocals of the pivots into the diagonal of lu
+  for (int col = lj; col < N; col += 2)
+    for (int i = li; i < N; i += 16) w.c[w.p[i] + N * col] = X[i + N * col];
+  for (int i = lane; i < rank; i += 32) lu[i + N * i] = cdiv(cmake(1.0, 0.0), lu[i + N * i]);
+  __syncwarp();
   // unit-lower forward substitution, column oriented
   for (int j = 0; j < N - 1; ++j) {
-    for (int e = tid; e < (N - 1 - j) * N; e += blockDim.x) {
-      const int i = j + 1 + e % (N - 1 - j), col = e / (N - 1 - j);
-      cmsub(w.c[i + N * col], lu[i + N * j], w.c[j + N * col]);
-    }
-    __syncthreads();
+    for (int col = lj; col < N; col += 2)
+      for (int i = j + 1 + li; i < N; i += 16) cmsub(w.c[i + N * col], lu[i + N * j], w.c[j + N * col]);
+    __syncwarp();
   }
   // upper backward substitution on the leading rank x rank block
   for (int i = rank - 1; i >= 0; --i) {
-    const cd d = lu[i + N * i];
-    for (int col = tid; col < N; col += blockDim.x) w.c[i + N * col] = cdiv(w.c[i + N * col], d);
-    __syncthreads();
-    for (int e = tid; e < i * N; e += blockDim.x) {
-      const int r = e % i, col = e / i;
-      cmsub(w.c[r + N * col], lu[r + N * i], w.c[i + N * col]);
+    const cd rd = lu[i + N * i];
+    for (int col = lane; col < N; col += 32) w.c[i + N * col] = cmul(w.c[i + N * col], rd);
+    __syncwarp();
+    for (int col = lj; col < N; col += 2)
+      for (int r = li; r < i; r += 16) cmsub(w.c[r + N * col], lu[r + N * i], w.c[i + N * col]);
+    __syncwarp();
+  }
+  for (int col = lj; col < N; col += 2)
+    for (int i = li; i < N; i += 16) X[w.q[i] + N * col] = (i < rank) ? w.c[i + N * col] : czero();
+}
+__device__ __forceinline__ void sm_lu_solve(cd* X, cd* lu, const LuWork& w, int N) {
+  if (threadIdx.x < 32) warp_lu_solve(X, lu, w, N);
+  __syncthreads();
+}
+
+// Inverse by Gauss-Jordan elimination with row pivoting, one matrix entry per thread and one
+// CTA barrier per column.  This replaces the reference's fullPivLu().solve(I)
+// (block_solvers.hpp:142,166) on the device: a sequential full-pivot LU is a chain of ~10 N
+// dependent steps in one warp (measured 90k cycles at N = 12, i.e. ~45 us in every iteration),
+// the elimination below exposes N^2-way parallelism and takes a few microseconds.  Both are
+// backward stable on the matrices of this path (alpha^-1 = P^dag T is Hermitian positive
+// definite, beta_s^-1 = I + O(shift) perturbation); Eigen's rank truncation of pivots below
+// eps * N * |maxpivot| (FullPivLU.h:317-341) is NOT reproduced: a vanishing pivot raises
+// *s_info instead (divergence documented in DESIGN.md).
+// piv: N ints of scratch; s_info: -1 on success, else the column whose pivot column vanished.
+// The elimination ping-pongs between A and the scratch matrix W (one barrier per column);
+// every warp finds the pivot row itself (16 candidates per shuffle tree, no hand-off).
+// PIVOT = false takes the diagonal entry (Hermitian positive definite input).
+template <bool PIVOT>
+__device__ __noinline__ void sm_inverse(cd* A, cd* W, int N, int* piv, int* s_info) {
+  const int tid = threadIdx.x, lane = tid & 31, nn = N * N;
+  if (tid == 0) *s_info = -1;
+  cd* src = A;
+  cd* dst = W;
+  for (int k = 0; k < N; ++k) {
+    int br = k;
+    if (PIVOT) {  // largest |A(r,k)|, r >= k, first one on ties
+      double bv = -1.0;
+      for (int r = k + lane; r < N; r += 32) {
+        const double a = cabs2(src[r + N * k]);
+        if (a > bv) {
+          bv = a;
+          br = r;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, br, off);
+        if (ov > bv || (ov == bv && orow < br)) {
+          bv = ov;
+          br = orow;
+        }
+      }
+      if (tid == 0) piv[k] = br;
+    }
+    const cd pk = src[br + N * k];
+    const double pa = cabs2(pk);
+    if (tid == 0 && !(pa > 0.0)) *s_info = k;
+    const double pn = 1.0 / pa;
+    const cd rp = cmake(pk.x * pn, -pk.y * pn);  // 1 / pivot
+    for (int e = tid; e < nn; e += blockDim.x) {
+      BCG_IJ(e, i, j);
+      const int si = (i == k) ? br : (i == br) ? k : i;  // source row after the exchange k <-> br
+      cd v;
+      if (i == k) {
+        v = (j == k) ? rp : cmul(src[br + N * j], rp);
+      } else if (j == k) {
+        const cd aik = src[si + N * k];
+        v = cmul(cmake(-aik.x, -aik.y), rp);
+      } else {
+        v = src[si + N * j];
+        cmsub(v, cmul(src[si + N * k], rp), src[br + N * j]);
+      }
+      dst[e] = v;
     }
     __syncthreads();
+    cd* t = src;
+    src = dst;
+    dst = t;
   }
-  for (int e = tid; e < N * N; e += blockDim.x) {
-    const int i = e % N, col = e / N;
-    X[w.q[i] + N * col] = (i < rank) ? w.c[i + N * col] : czero();
+  if (PIVOT) {
+    // undo the row exchanges as column exchanges, last first
+    for (int k = N - 1; k >= 0; --k) {
+      const int br = piv[k];
+      if (br != k) {
+        for (int i = tid; i < N; i += blockDim.x) {
+          const cd t = src[i + N * k];
+          src[i + N * k] = src[i + N * br];
+          src[i + N * br] = t;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (src != A) {
+    for (int e = tid; e < nn; e += blockDim.x) A[e] = src[e];
   }
   __syncthreads();
 }
@@ -350,7 +467,7 @@ __global__ void __launch_bounds__(kSmallThreads)
 gram_reduce_kernel(cd* __restrict__ out, const cd* __restrict__ gpart, int nparts, int N) {
   extern __shared__ __align__(16) unsigned char raw[];
   cd* G = reinterpret_cast<cd*>(raw);
-  sm_reduce_gram(G, gpart, nparts, N);
+  sm_reduce_gram(G, gpart, nparts, N, G + N * N);
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) out[e] = G[e];
 }
 
@@ -360,6 +477,7 @@ chol_kernel(cd* __restrict__ R, const cd* __restrict__ G, int N, Ctrl* __restric
   extern __shared__ __align__(16) unsigned char raw[];
   SmallSmem s;
   s.carve(raw, N);
+  sm_init_ij(N);
   sm_copy(s.mat[0], G, N * N);
   const int info = sm_chol_upper(s.mat[1], s.mat[0], s.mat[2], N, s.info);
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) R[e] = s.mat[1][e];
@@ -376,7 +494,8 @@ rq_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm, 
   const int N = L.N, nn = N * N;
   SmallSmem s;
   s.carve(raw, N);
-  sm_reduce_gram(s.mat[0], gpart, nparts, N);
+  sm_init_ij(N);
+  sm_reduce_gram(s.mat[0], gpart, nparts, N, s.mat[4]);
   const int info = sm_chol_upper(s.mat[1], s.mat[0], s.mat[2], N, s.info);
   sm_identity(s.mat[3], N);
   sm_rownorms(s.vec, s.mat[1], N);
@@ -385,7 +504,7 @@ rq_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm, 
     mats[L.fixed(M_DELTA) + e] = d;
     mats[L.fixed(M_RHO0) + e] = d;
     mats[L.fixed(M_RHO1) + e] = d;
-    mats[L.fixed(M_RHO_CUR) + e] = ((e % N) == (e / N)) ? cdiv(cmake(1.0, 0.0), d) : d;
+    mats[L.fixed(M_RHO_CUR) + e] = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? cdiv(cmake(1.0, 0.0), d) : d;
     mats[L.fixed(M_ALPHA_INV0) + e] = id;
     mats[L.fixed(M_ALPHA_INV1) + e] = id;
     for (int sh = 0; sh < L.S; ++sh) {
@@ -416,6 +535,7 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   const int N = L.N, nn = N * N;
   SmallSmem s;
   s.carve(raw, N);
+  sm_init_ij(N);
   const int iter = ctrl->iter + 1;
   const int n_unconv_old = ctrl->n_unconv;
   __syncthreads();
@@ -437,18 +557,40 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   cd* alpha = s.mat[2];
   cd* delta = s.mat[3];
   cd* ad = s.mat[4];
-  sm_reduce_gram(Ainv, gpart, nparts, N);
-  sm_copy(lu, Ainv, nn);
-  sm_identity(alpha, N);
-  sm_lu_solve(alpha, lu, s.lw, N);
+#ifdef BCG_DEBUG_TIMING
+  long long tt[6];
+  tt[0] = clock64();
+#endif
+  sm_reduce_gram(Ainv, gpart, nparts, N, s.mat[4]);
+#ifdef BCG_DEBUG_TIMING
+  tt[1] = clock64();
+#endif
+  sm_copy(alpha, Ainv, nn);
+#ifdef BCG_DEBUG_TIMING
+  tt[2] = clock64();
+#endif
+  sm_inverse<false>(alpha, lu, N, s.lw.rt, s.info);  // alpha = (P0^dag T)^-1, Hermitian positive definite
+  if (threadIdx.x == 0 && *s.info >= 0) {  // singular P0^dag T: the operator is not positive definite
+    ctrl->status = 3;
+    ctrl->stop = 1;
+  }
+#ifdef BCG_DEBUG_TIMING
+  tt[3] = clock64();
+#endif
   sm_copy(delta, mats + L.fixed(M_DELTA), nn);
   sm_mm(ad, alpha, delta, N);
+#ifdef BCG_DEBUG_TIMING
+  tt[4] = clock64();
+  if (threadIdx.x == 0 && iter <= 6)
+    printf("step_a it %d: reduce %lld copy %lld lu %lld mm %lld (clk)\n", iter, tt[1] - tt[0], tt[2] - tt[1],
+           tt[3] - tt[2], tt[4] - tt[3]);
+#endif
   cd* ainv_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     ainv_g[e] = Ainv[e];
     mats[L.fixed(M_ALPHA) + e] = alpha[e];
     mats[L.fixed(M_NEGALPHA) + e] = cmake(-alpha[e].x, -alpha[e].y);
-    mats[L.A(0) + shift_mat_index(N, e % N, e / N)] = ad[e];
+    mats[L.A(0) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = ad[e];
   }
 }
 
@@ -468,11 +610,12 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   const int N = L.N, nn = N * N;
   SmallSmem s;
   s.carve(raw, N);
+  sm_init_ij(N);
   const int iter = ctrl->iter;
   cd* G = s.mat[0];
   cd* rho = s.mat[1];
   cd* t0 = s.mat[2];
-  sm_reduce_gram(G, gpart, nparts, N);
+  sm_reduce_gram(G, gpart, nparts, N, s.mat[4]);
   const int info = sm_chol_upper(rho, G, t0, N, s.info);
   cd* rho_g = mats + L.fixed((iter & 1) ? M_RHO1 : M_RHO0);
   const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
@@ -483,7 +626,7 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
     sm_mm(dn, rho, delta, N);
     sm_rownorms(s.vec, dn, N);
     for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-      const int i = e % N, j = e / N;
+      BCG_IJ(e, i, j);
       rho_g[e] = rho[e];
       mats[L.fixed(M_RHO_CUR) + e] = (i == j) ? cdiv(cmake(1.0, 0.0), rho[e]) : rho[e];
       mats[L.fixed(M_DELTA) + e] = dn[e];
@@ -533,7 +676,7 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   sm_mm(t1, alpha, rho_old, N);
   sm_mm(t2, t1, ainv_old, N);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    const double id = ((e % N) == (e / N)) ? 1.0 : 0.0;
+    const double id = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? 1.0 : 0.0;
     t1[e] = cmake(id - beta[e].x, -beta[e].y);
   }
   __syncthreads();
@@ -541,11 +684,11 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   sm_mm_adj(t1, G, rho_old, N);  // ... * rho_old^dag
   const double ds = ctrl->sigma[sh] - ctrl->sigma[0];
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    const double id = ((e % N) == (e / N)) ? 1.0 : 0.0;
+    const double id = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? 1.0 : 0.0;
     lu[e] = cmake((id + ds * alpha[e].x) + t1[e].x, (ds * alpha[e].y) + t1[e].y);
   }
-  sm_identity(beta, N);
-  sm_lu_solve(beta, lu, s.lw, N);  // beta_s = beta_s_inv^-1
+  sm_copy(beta, lu, nn);
+  sm_inverse<true>(beta, lu, N, s.lw.rt, s.info);  // beta_s = beta_s_inv^-1 (general complex matrix)
   // alpha_s = beta_s alpha rho_old alpha_inv_old alpha_s  (left to right)
   sm_mm(t1, beta, alpha, N);
   sm_mm(t2, t1, rho_old, N);
@@ -559,8 +702,8 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     mats[L.alpha_s(sh) + e] = t2[e];
     mats[L.beta_s(sh) + e] = beta[e];
-    mats[L.A(sh) + shift_mat_index(N, e % N, e / N)] = t2[e];
-    mats[L.B(sh) + shift_mat_index(N, e % N, e / N)] = t1[e];
+    mats[L.A(sh) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = t2[e];
+    mats[L.B(sh) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = t1[e];
   }
   if (threadIdx.x == 0) {
     double r = 0.0;
@@ -579,7 +722,8 @@ bcg_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm,
   const int N = L.N, nn = N * N;
   SmallSmem s;
   s.carve(raw, N);
-  sm_reduce_gram(s.mat[0], gpart, nparts, N);
+  sm_init_ij(N);
+  sm_reduce_gram(s.mat[0], gpart, nparts, N, s.mat[4]);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) mats[L.fixed(M_R2) + e] = s.mat[0][e];
   for (int i = threadIdx.x; i < N; i += blockDim.x) b_norm[i] = sqrt(s.mat[0][i + N * i].x);
 }
@@ -597,17 +741,18 @@ bcg_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpa
   const int N = L.N, nn = N * N;
   SmallSmem s;
   s.carve(raw, N);
+  sm_init_ij(N);
   const int iter = ctrl->iter + 1;
   __syncthreads();
   if (threadIdx.x == 0) ctrl->iter = iter;
-  sm_reduce_gram(s.mat[0], gpart, nparts, N);
+  sm_reduce_gram(s.mat[0], gpart, nparts, N, s.mat[4]);
   sm_copy(s.mat[1], mats + L.fixed(M_R2), nn);  // X enters as B = r2
   sm_lu_solve(s.mat[1], s.mat[0], s.lw, N);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     const cd a = s.mat[1][e];
     mats[L.fixed(M_ALPHA) + e] = a;
     mats[L.fixed(M_NEGALPHA) + e] = cmake(-a.x, -a.y);
-    mats[L.A(0) + shift_mat_index(N, e % N, e / N)] = a;
+    mats[L.A(0) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = a;
   }
 }
 // B-step: r2_old = r2 ; r2 = R^dag R ; beta = LU(r2_old).solve(r2) ; residual ; B_0 = beta
@@ -619,16 +764,17 @@ bcg_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__
   const int N = L.N, nn = N * N;
   SmallSmem s;
   s.carve(raw, N);
+  sm_init_ij(N);
   cd* r2 = s.mat[0];
   cd* r2old = s.mat[1];
   cd* beta = s.mat[2];
-  sm_reduce_gram(r2, gpart, nparts, N);
+  sm_reduce_gram(r2, gpart, nparts, N, s.mat[4]);
   sm_copy(r2old, mats + L.fixed(M_R2), nn);
   sm_copy(beta, r2, nn);
   sm_lu_solve(beta, r2old, s.lw, N);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     mats[L.fixed(M_R2) + e] = r2[e];
-    mats[L.B(0) + shift_mat_index(N, e % N, e / N)] = beta[e];
+    mats[L.B(0) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = beta[e];
   }
   if (threadIdx.x == 0) {
     double r = 0.0;
