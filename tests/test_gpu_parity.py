@@ -143,6 +143,57 @@ def test_primitives_vs_oracle_larger(bcg, oracle, V, N):
         assert np.abs(ctx.gram(hw, hw) - np.eye(N)).max() < 1e-12
 
 
+@pytest.mark.parametrize("N", [4, 8, 12])
+@pytest.mark.parametrize("V", [1, 2, 3, 5, 31, 47, 4737, 9475])
+def test_pipeline_kernels_ragged(bcg, oracle, V, N):
+    """The warp-specialised kernels (parity-chain stencil, pipelined Q += T*M, tensor-map
+    multishift update) at sizes that leave empty sub-chains, half-filled windows, a last site
+    pair that is half halo, and a grid smaller / larger than the SM count."""
+    rng = np.random.default_rng(7 * V + N)
+    U, B = oracle.make_inputs(V, N, 5)
+    mass = 0.4
+    M = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+    with bcg.Context(V, N) as ctx:
+        ctx.set_links(U, mass)
+        hb, hab, hw = ctx.field(B), ctx.field(), ctx.field()
+        G = ctx.op(hab, hb, sigma=0.5, want_gram=True)
+        AB = oracle.op(U, B, mass, 0.5)
+        assert rel(ctx.download(hab), AB) < 1e-13
+        assert rel(G, oracle.hermitian_dot(B, AB)) < 1e-12
+        ctx.op(hw, hb, sigma=0.5)  # without the Gram epilogue: same field, bit for bit
+        assert np.array_equal(ctx.download(hw), ctx.download(hab))
+        ctx.upload(hw, B)
+        ctx.add(hw, hab, M)
+        assert rel(ctx.download(hw), oracle.add(B, AB, M)) < 1e-13
+        if V * 3 >= 2 * N:  # otherwise B^dag B is (nearly) singular and there is nothing to compare
+            ctx.upload(hw, B)
+            R = ctx.thinqr(hw)
+            Q, Ro = oracle.thinQR(B)
+            assert rel(R, Ro) < 1e-10 and rel(ctx.download(hw), Q) < 1e-9
+
+
+def test_reductions_are_bit_reproducible(bcg, oracle):
+    """Two-level Gram reduction (per-CTA blocks, last group member adds its group, fixed-order
+    final sum): no floating-point atomics, so repeated runs agree bit for bit -- fused
+    epilogues and full solves alike."""
+    V, N, mass = 40000, 12, 0.05
+    U, B = oracle.make_inputs(V, N, 2)
+    shifts = [0.0, 1e-3, 1e-1]
+    outs = []
+    for _ in range(3):
+        with bcg.Context(V, N, max_shifts=3) as ctx:
+            ctx.set_links(U, mass)
+            hb, ha = ctx.field(B), ctx.field()
+            G = ctx.op(ha, hb, want_gram=True)
+            xs = [ctx.field() for _ in shifts]
+            info = ctx.solve_sbcgrq_dev(xs, hb, shifts, 1e-8, 1e-15, 60)
+            outs.append((G, info.iterations, [ctx.download(x) for x in xs]))
+    for G, it, X in outs[1:]:
+        assert np.array_equal(G, outs[0][0]) and it == outs[0][1]
+        for a, b in zip(X, outs[0][2]):
+            assert np.array_equal(a, b)
+
+
 def test_full_size_properties(bcg, oracle):
     """BASELINE config sizes (16^4, N=12): properties that need no CPU solve."""
     V, N, mass = 16 ** 4, 12, 1e-3
