@@ -1,0 +1,40 @@
+"""GPU tests (-m gpu) of the C++ host mirror: the reference's own regression suite
+(test/solvers.cpp: V=128, mass 0.5, N_rhs=3, 5 shifts, every true residual < 2*eps) and
+its benchmark program (benchmark.cpp, README.md:29 defaults) rebuilt against
+blockcg_b200/host/*.hpp + libblockcg_b200.so, run as the reference's users run them."""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HOST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "blockcg_b200", "host")
+
+
+def _binary(name):
+    path = os.path.join(HOST, name)
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", HOST, name], check=True)
+    return path
+
+
+def test_reference_regression_suite():
+    out = subprocess.run([_binary("test_solvers")], capture_output=True, text=True, timeout=600)
+    print(out.stdout[-2000:])
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "27" in out.stdout  # 1 + 5 + 3 + 3 + 15 assertions, as in the reference
+
+
+def test_benchmark_program_readme_config():
+    out = subprocess.run([_binary("benchmark"), "1e3", "1e-3", "1e-10"], capture_output=True, text=True, timeout=900)
+    print(out.stdout[-2000:])
+    assert out.returncode == 0, out.stderr[-2000:]
+    it = int(re.search(r"SBCGrQ_iterations:\s+(\d+)", out.stdout).group(1))
+    # reference: 12 x 444; the tree-shaped Gram converges a few % sooner (F7b)
+    assert 12 * 400 <= it <= 12 * 446, it
+    res = [float(x) for x in re.search(r"SBCGrQ residuals:\s+(.*)", out.stdout).group(1).split()]
+    assert len(res) == 9 and max(res) < 1e-9
+    scg = [float(x) for x in re.search(r"SCG residuals:\s+(.*)", out.stdout).group(1).split()]
+    assert len(scg) == 9 and max(scg) < 1e-8
