@@ -103,6 +103,7 @@ struct Tune {
   // rhs columns per stencil work item (must divide N)
   static constexpr int R = (N % 3 == 0) ? 3 : (N % 2 == 0) ? 2 : 1;
   // parity-chain stencil (dirac_chain.cuh): column groups per site, 0 = not used at this N
+  // (N = 16 would need a finer split of the Gram: 36 accumulators per warp do not fit in registers)
   static constexpr int CHAIN_G = (N % 4 == 0 && N <= 12) ? 4 : 0;
   static constexpr int CHAIN_K = 16;  // sub-chains per CTA
   static constexpr int CHAIN_W = 2;   // sites per sub-chain and tile
@@ -127,8 +128,9 @@ struct Ops {
   static constexpr size_t SHIFT_SMEM = sizeof(cd) * 5 * N * N;
   static constexpr int SHIFT_TS = 32;  // sites per pipeline tile
   using SG = ShiftGeom<N, SHIFT_TS>;
-  static constexpr bool PIPE_OK = SG::SMEM_BYTES <= 227 * 1024;
-  static constexpr bool APIPE = (N % 2 == 0 && N >= 4);  // pipelined Q += T*M (axpy_pipe.cuh)
+  // a tensor-map box row (one padded site pair, in doubles) may not exceed 256 elements
+  static constexpr bool PIPE_OK = SG::SMEM_BYTES <= 227 * 1024 && 2 * SG::PAIR <= 256;
+  static constexpr bool APIPE = (N % 2 == 0 && N >= 4 && N <= 12);  // pipelined Q += T*M (axpy_pipe.cuh)
   static constexpr int APIPE_TS = 32;
   using APG = AxpyPipeGeom<APIPE ? N : 4, APIPE_TS>;
   static constexpr bool CHAIN = Tune<N>::CHAIN_G > 0;

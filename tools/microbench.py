@@ -15,6 +15,25 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import blockcg_b200  # noqa: E402
 
 
+def sweep(V, N, reps, seed=0):
+    """BASELINE configs[4]: block Dirac apply / Gram / fused update at one (V, N); three fields only."""
+    rng = np.random.default_rng(seed)
+    U = rng.uniform(-1, 1, (V, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 3, 3))
+    F, Ub = 48.0 * N * V, 144.0 * V
+    out = {"V": V, "N": N}
+    with blockcg_b200.Context(V, N, max_shifts=1) as ctx:
+        ctx.set_links(U, 1e-3)
+        data = rng.uniform(-1, 1, (V, N, 3)) + 1j * rng.uniform(-1, 1, (V, N, 3))
+        hs = [ctx.field(data), ctx.field(data), ctx.field()]
+        del data
+        for name, which, nh, nbytes in [("dirac", 1, 2, 2 * F + Ub), ("dirac_gram", 0, 2, 2 * F + Ub),
+                                        ("gram", 2, 2, 2 * F), ("axpy_gram", 3, 2, 3 * F),
+                                        ("shift_update_S1", 4, 3, 6 * F)]:
+            ms, _ = ctx.bench_kernel(which, reps, hs[:nh], 1)
+            out[name] = {"us": round(1e3 * ms, 1), "GBps": round(nbytes / ms / 1e6)}
+    return out
+
+
 def run(V, N, S, reps, seed=0):
     rng = np.random.default_rng(seed)
     U = rng.uniform(-1, 1, (V, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 3, 3))
@@ -55,7 +74,13 @@ if __name__ == "__main__":
     ap.add_argument("--N", type=int, nargs="+", default=[12])
     ap.add_argument("--S", type=int, default=9)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--sweep", action="store_true", help="Dirac / Gram / update sweep over (V, N), 3 fields")
     a = ap.parse_args()
+    if a.sweep:
+        for V in a.V:
+            for N in a.N:
+                print(json.dumps(sweep(V, N, a.reps)), flush=True)
+        sys.exit(0)
     for V in a.V:
         for N in a.N:
             print(json.dumps(run(V, N, a.S, a.reps)), flush=True)
