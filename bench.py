@@ -157,7 +157,7 @@ def run_reference(args, w, wname):
 def config_of(wname, w, gpus):
     return {"workload": wname, "V": w["V"], "n_rhs": w["N"], "n_shifts": len(w["shifts"]), "mass": w["mass"],
             "eps": w["eps"], "eps_shifts": w["eps_shifts"], "operator": "reference 1-D chain (inc/dirac_op.hpp:13-21)",
-            "partition": "1 slab" if gpus == 1 else "%d contiguous site slabs, NCCL halo + Gram allreduce" % gpus,
+            "partition": "1 slab" if gpus == 1 else "%d contiguous site slabs; halo sites and Gram blocks exchanged by P2P stores over NVLink from inside the kernels (NCCL only in the set-up)" % gpus,
             "l2_policy": ("%d fields of %.0f MB each per GPU stream through every iteration (working set %s the"
                           " 126 MB L2); no explicit flush"
                           % (2 * len(w["shifts"]) + 2, 48.0 * w["N"] * w["V"] / gpus / 1e6,
@@ -201,6 +201,9 @@ def run_ours(args, w, wname):
             uid.copy_(torch.frombuffer(bytearray(ctx.unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        if not args.no_p2p:
+            from blockcg_b200.distributed import exchange_ipc_handles
+            exchange_ipc_handles(dist, ctx, torch.device("cuda", local))
     ctx.set_links(Ul, w["mass"])
 
     def barrier():
@@ -331,6 +334,7 @@ def main():
     ap.add_argument("--max-it", type=int, default=1000000)
     ap.add_argument("--cpu-iters", type=int, default=4, help="iterations in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL halo / all-reduce instead of peer-memory stores")
     ap.add_argument("--record-iterations", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

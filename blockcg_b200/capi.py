@@ -17,6 +17,7 @@ _ip = C.POINTER(C.c_int)
 
 MAX_SHIFTS = 32
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 STATUS = {0: "BCG_OK", 1: "BCG_ERR_INVALID", 2: "BCG_ERR_CUDA", 3: "BCG_ERR_NOT_PD", 4: "BCG_ERR_NCCL",
           5: "BCG_ERR_NO_COMM", 6: "BCG_ERR_NAN"}
@@ -24,7 +25,7 @@ STATUS = {0: "BCG_OK", 1: "BCG_ERR_INVALID", 2: "BCG_ERR_CUDA", 3: "BCG_ERR_NOT_
 # every symbol include/blockcg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "bcg_version", "bcg_supports_nrhs", "bcg_ctx_create", "bcg_ctx_destroy", "bcg_last_error",
-    "bcg_comm_get_unique_id", "bcg_comm_init", "bcg_set_links", "bcg_field_alloc", "bcg_field_free",
+    "bcg_comm_get_unique_id", "bcg_comm_init", "bcg_comm_ipc_handle", "bcg_comm_ipc_open", "bcg_set_links", "bcg_field_alloc", "bcg_field_free",
     "bcg_field_upload", "bcg_field_download", "bcg_field_zero", "bcg_field_copy", "bcg_op", "bcg_gram",
     "bcg_add", "bcg_add_scalar", "bcg_rescale_add", "bcg_trsm", "bcg_thinqr", "bcg_true_residual",
     "bcg_solve_bcg_dev", "bcg_solve_bcgrq_dev", "bcg_solve_sbcgrq_dev", "bcg_solve_bcg", "bcg_solve_bcgrq",
@@ -68,6 +69,8 @@ def load():
     lib.bcg_ctx_destroy.argtypes = [C.c_void_p]
     lib.bcg_comm_get_unique_id.argtypes = [C.c_void_p]
     lib.bcg_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bcg_comm_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bcg_comm_ipc_open.argtypes = [C.c_void_p, C.c_void_p]
     lib.bcg_set_links.argtypes = [C.c_void_p, _dp, C.c_double]
     lib.bcg_field_alloc.argtypes = [C.c_void_p, _ip]
     lib.bcg_field_free.argtypes = [C.c_void_p, C.c_int]
@@ -154,6 +157,17 @@ class Context:
         if rc:
             raise BcgError(rc, "ncclGetUniqueId failed")
         return bytes(buf.raw)
+
+    def ipc_handle(self):
+        """CUDA-IPC handle of this rank's communication buffer (peer-memory exchange over NVLink)."""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._ck(self.lib.bcg_comm_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def ipc_open(self, handles):
+        """handles: the ipc_handle() of every rank, concatenated in rank order."""
+        buf = C.create_string_buffer(bytes(handles), len(handles))
+        self._ck(self.lib.bcg_comm_ipc_open(self._h, buf))
 
     def comm_init(self, uid):
         buf = C.create_string_buffer(bytes(uid), UNIQUE_ID_BYTES)

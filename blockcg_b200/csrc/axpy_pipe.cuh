@@ -44,7 +44,8 @@ struct AxpyPipeGeom {
 template <int N, int TS, bool GRAM>
 __global__ void __launch_bounds__(AxpyPipeGeom<N, TS>::NT, 1)
 axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT,
-                 const cd* __restrict__ M, long long V, cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl) {
+                 const cd* __restrict__ M, long long V, cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl,
+                 const GramPeers peers) {
   using Geo = AxpyPipeGeom<N, TS>;
   constexpr int NSPLIT = Geo::NSPLIT, JC = Geo::JC, SPW = Geo::SPW, NCW = Geo::NCW, SITE = Geo::SITE;
   constexpr int PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE, NS = Geo::NSTAGE;
@@ -140,7 +141,7 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       // scratch: the T tile of stage (warp - NCW); every update has finished with it by now
       part.store(gpart + (static_cast<size_t>(kGramRawOff) + blockIdx.x) * N * N, sbuf + (warp - NCW) * STAGE);
-      gram_group_reduce<N>(gpart, warp - NCW);
+      gram_group_reduce<N>(gpart, warp - NCW, peers, ctrl, 1);
     };
     switch (warp - NCW) {
       case 0: { GramPart<N, 0> part; gram_loop(part); break; }

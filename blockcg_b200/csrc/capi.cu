@@ -130,6 +130,11 @@ struct bcg_ctx {
   cudaEvent_t ev_batch[2] = {nullptr, nullptr};
   ncclComm_t comm = nullptr;
   bool comm_ready = false;
+  // peer-memory exchange (CUDA IPC over NVLink): this rank's buffer and the peers' mappings of theirs
+  unsigned char* p2p_local = nullptr;
+  unsigned char* p2p_peer[kMaxRanks] = {};
+  bool p2p_ready = false;
+  unsigned epoch = 0;  // solves started on this context (sequence-number base of the exchange)
   GraphCache graph;
   std::string err;
   size_t small_smem = 0;
@@ -178,6 +183,58 @@ inline bool valid(const bcg_ctx* c, int h) {
 }
 inline cd* mat(const bcg_ctx* c, int slot) { return c->mats + c->L.fixed(slot); }
 
+// layout of a rank's communication buffer (bytes)
+struct P2PLayout {
+  size_t nn, site;
+  size_t gram_blocks(int ch) const { return ch * 2 * kMaxRanks * nn * sizeof(cd); }          // [2][kMaxRanks][nn]
+  size_t gram_seq(int ch) const { return 2 * 2 * kMaxRanks * nn * sizeof(cd) + ch * kMaxRanks * 8; }
+  size_t halo(int side) const {  // side 0: "from the left" (my slots -2,-1), 1: "from the right" (V, V+1); [2][2 sites]
+    return 2 * 2 * kMaxRanks * nn * sizeof(cd) + 2 * kMaxRanks * 8 + side * 2 * 2 * site * sizeof(cd);
+  }
+  size_t halo_seq(int side) const { return halo(2) + side * 8; }
+  size_t total() const { return (halo_seq(2) + 255) / 256 * 256; }
+};
+inline P2PLayout p2p_layout(const bcg_ctx* c) { return P2PLayout{c->L.nn(), static_cast<size_t>(3) * c->N}; }
+
+GramPeers gram_peers(const bcg_ctx* c, int ch) {
+  GramPeers g;
+  std::memset(&g, 0, sizeof g);
+  if (!c->p2p_ready) return g;
+  const P2PLayout l = p2p_layout(c);
+  for (int r = 0; r < c->nranks; ++r) {
+    g.slot[r] = reinterpret_cast<cd*>(c->p2p_peer[r] + l.gram_blocks(ch));
+    g.seq[r] = reinterpret_cast<unsigned long long*>(c->p2p_peer[r] + l.gram_seq(ch));
+  }
+  g.nranks = c->nranks;
+  g.rank = c->rank;
+  return g;
+}
+GramWait gram_wait(const bcg_ctx* c, int ch) {
+  GramWait w;
+  std::memset(&w, 0, sizeof w);
+  if (!c->p2p_ready) return w;
+  const P2PLayout l = p2p_layout(c);
+  w.slots = reinterpret_cast<const cd*>(c->p2p_local + l.gram_blocks(ch));
+  w.seq = reinterpret_cast<const unsigned long long*>(c->p2p_local + l.gram_seq(ch));
+  w.nranks = c->nranks;
+  return w;
+}
+HaloPeers halo_peers(const bcg_ctx* c) {
+  HaloPeers h;
+  std::memset(&h, 0, sizeof h);
+  const P2PLayout l = p2p_layout(c);
+  const int left = (c->rank + c->nranks - 1) % c->nranks, right = (c->rank + 1) % c->nranks;
+  h.lo_of_right = reinterpret_cast<cd*>(c->p2p_peer[right] + l.halo(0));
+  h.hi_of_left = reinterpret_cast<cd*>(c->p2p_peer[left] + l.halo(1));
+  h.seq_lo_of_right = reinterpret_cast<unsigned long long*>(c->p2p_peer[right] + l.halo_seq(0));
+  h.seq_hi_of_left = reinterpret_cast<unsigned long long*>(c->p2p_peer[left] + l.halo_seq(1));
+  h.my_lo = reinterpret_cast<const cd*>(c->p2p_local + l.halo(0));
+  h.my_hi = reinterpret_cast<const cd*>(c->p2p_local + l.halo(1));
+  h.my_seq_lo = reinterpret_cast<const unsigned long long*>(c->p2p_local + l.halo_seq(0));
+  h.my_seq_hi = reinterpret_cast<const unsigned long long*>(c->p2p_local + l.halo_seq(1));
+  return h;
+}
+
 int field_alloc(bcg_ctx* c, int* h) {
   cd* p = nullptr;
   CU(cudaMalloc(&p, field_elems(c) * sizeof(cd)));
@@ -202,8 +259,18 @@ int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
     CU(cudaGetLastError());
     return BCG_OK;
   }
-  if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
   if (c->V < 2) return fail(c, BCG_ERR_INVALID, "slab decomposition needs >= 2 sites per rank");
+  if (c->p2p_ready && ctrl != nullptr && site == 3 * c->N) {
+    // inside the iteration loop: boundary sites go straight into the neighbours' buffers over
+    // NVLink (P2P stores + sequence word), the receiver copies them into its halo slots
+    const HaloPeers hp = halo_peers(c);
+    halo_push_kernel<<<1, 128, 0, c->stream>>>(f, c->V, site, hp, ctrl);
+    halo_wait_unpack_kernel<<<1, 128, 0, c->stream>>>(f, c->V, site, hp, const_cast<Ctrl*>(ctrl));
+    if (launches) *launches += 2;
+    CU(cudaGetLastError());
+    return BCG_OK;
+  }
+  if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
   const int left = (c->rank + c->nranks - 1) % c->nranks, right = (c->rank + 1) % c->nranks;
   const size_t cnt = static_cast<size_t>(2) * site * 2;  // doubles
   // boundary sites are contiguous in the field and halo slots are contiguous too:
@@ -221,8 +288,8 @@ int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
 // partials themselves (reduced in fixed order inside the coefficient kernel).
 // Multi rank: reduce locally, all-reduce the N x N block over NVLink, hand the
 // kernels one "partial".
-int gram_finalize(bcg_ctx* c, int nparts, const cd** src, int* nsrc, int* launches) {
-  if (c->nranks == 1) {
+int gram_finalize(bcg_ctx* c, int nparts, const cd** src, int* nsrc, int* launches, bool fused_exchange = false) {
+  if (c->nranks == 1 || fused_exchange) {  // fused_exchange: the producing kernel has pushed the block to all peers
     *src = c->gpart;
     *nsrc = nparts;
     return BCG_OK;
@@ -364,6 +431,9 @@ int bcg_ctx_destroy(bcg_ctx* c) {
   }
   if (c->graph.exec) cudaGraphExecDestroy(c->graph.exec);
   if (c->comm) ncclCommDestroy(c->comm);
+  for (int r = 0; r < c->nranks && r < kMaxRanks; ++r)
+    if (c->p2p_peer[r] && c->p2p_peer[r] != c->p2p_local) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+  if (c->p2p_local) cudaFree(c->p2p_local);
   for (cd* p : c->fields)
     if (p) cudaFree(p);
   cudaFree(c->U_alloc);
@@ -402,6 +472,42 @@ int bcg_comm_init(bcg_ctx* c, const void* id_in) {
   std::memcpy(&id, id_in, sizeof id);
   NC(ncclCommInitRank(&c->comm, c->nranks, id, c->rank));
   c->comm_ready = true;
+  return BCG_OK;
+}
+
+int bcg_comm_ipc_handle(bcg_ctx* c, void* handle_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) <= BCG_IPC_HANDLE_BYTES, "handle size");
+  if (!c || !handle_out) return BCG_ERR_INVALID;
+  if (c->nranks > kMaxRanks) return fail(c, BCG_ERR_INVALID, "peer-memory exchange supports up to %d ranks", kMaxRanks);
+  CU(cudaSetDevice(c->device));
+  if (!c->p2p_local) {
+    const size_t bytes = p2p_layout(c).total();
+    CU(cudaMalloc(&c->p2p_local, bytes));
+    CU(cudaMemset(c->p2p_local, 0, bytes));
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, c->p2p_local));
+  std::memset(handle_out, 0, BCG_IPC_HANDLE_BYTES);
+  std::memcpy(handle_out, &h, sizeof h);
+  return BCG_OK;
+}
+
+int bcg_comm_ipc_open(bcg_ctx* c, const void* handles) {
+  if (!c || !handles) return BCG_ERR_INVALID;
+  if (!c->p2p_local) return fail(c, BCG_ERR_INVALID, "call bcg_comm_ipc_handle first");
+  CU(cudaSetDevice(c->device));
+  for (int r = 0; r < c->nranks; ++r) {
+    if (r == c->rank) {
+      c->p2p_peer[r] = c->p2p_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const unsigned char*>(handles) + static_cast<size_t>(r) * BCG_IPC_HANDLE_BYTES, sizeof h);
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->p2p_peer[r] = static_cast<unsigned char*>(ptr);
+  }
+  c->p2p_ready = true;
   return BCG_OK;
 }
 
@@ -464,7 +570,7 @@ int bcg_op(bcg_ctx* c, int out, int in, double sigma, double* gram_host) {
   int r = halo_refresh(c, fptr(c, in), 3 * c->N, nullptr, nullptr);
   if (r) return r;
   int np = c->ops->dirac(c->stream, fptr(c, in), fptr(c, out), uptr(c), c->V, c->mass * c->mass, sigma,
-                         gram_host ? c->gpart : nullptr, nullptr, c->sms, nullptr);
+                         gram_host ? c->gpart : nullptr, nullptr, c->sms, nullptr, nullptr);
   KL(np);
   if (gram_host) {
     const size_t nn = c->L.nn();
@@ -494,7 +600,7 @@ int bcg_add(bcg_ctx* c, int dst, int src, const double* m_host) {
   int r = upload_mat(c, M_SCRATCH, m_host, 0);
   if (r) return r;
   KL(c->ops->axpy_gram(c->stream, fptr(c, dst), fptr(c, src), mat(c, M_SCRATCH), c->V, nullptr, nullptr, c->sms,
-                       nullptr));
+                       nullptr, nullptr));
   CU(cudaStreamSynchronize(c->stream));
   return BCG_OK;
 }
@@ -556,7 +662,7 @@ int bcg_true_residual(bcg_ctx* c, int x, int b, double sigma, double* res_host) 
   if (r) return r;
   cd* T = fptr(c, c->work_T);
   KL(c->ops->dirac(c->stream, fptr(c, x), T, uptr(c), c->V, c->mass * c->mass, sigma, nullptr, nullptr, c->sms,
-                   nullptr));
+                   nullptr, nullptr));
   const long long n = c->V * static_cast<long long>(site_elems(c));
   sub_kernel<<<c->sms * 8, 256, 0, c->stream>>>(T, T, fptr(c, b), n);
   CU(cudaGetLastError());
@@ -595,26 +701,34 @@ struct LoopPlan {
 int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
   const cd* gsrc;
   int nsrc;
+  // slab decomposition with mapped peer buffers: the Gram kernels push their block to every
+  // rank themselves and the coefficient kernels wait for the sequence words -- no NCCL call,
+  // no extra reduction kernel in the loop
+  const bool fused = c->nranks > 1 && c->p2p_ready && c->ops->fused_exchange;
+  const GramPeers gp0 = fused ? gram_peers(c, 0) : GramPeers{}, gp1 = fused ? gram_peers(c, 1) : GramPeers{};
+  const GramWait gw0 = fused ? gram_wait(c, 0) : GramWait{}, gw1 = fused ? gram_wait(c, 1) : GramWait{};
   int np = c->ops->dirac(c->stream, p.P0, p.T, uptr(c), c->V, c->mass * c->mass, p.sigma0, c->gpart, c->ctrl,
-                         c->sms, launches);
+                         c->sms, launches, fused ? &gp0 : nullptr);
   KL(np);
-  int r = gram_finalize(c, np, &gsrc, &nsrc, launches);
+  int r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
   if (p.kind == 1)
-    rq_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl);
+    rq_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   else
-    bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl);
+    bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   ++*launches;
   CU(cudaGetLastError());
-  np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches);
+  np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches,
+                         fused ? &gp1 : nullptr);
   KL(np);
-  r = gram_finalize(c, np, &gsrc, &nsrc, launches);
+  r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
   if (p.kind == 1)
     rq_step_b_kernel<<<p.n_shifts, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc,
-                                                                             c->ctrl);
+                                                                             c->ctrl, gw1);
   else
-    bcg_step_b_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc, c->ctrl);
+    bcg_step_b_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc, c->ctrl,
+                                                                      gw1);
   ++*launches;
   CU(cudaGetLastError());
   KL(c->ops->shift_update(c->stream, p.Q, &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
@@ -698,6 +812,7 @@ int init_ctrl(bcg_ctx* c, int n_shifts, const double* sigma, double eps, double 
   h.eps = eps;
   h.eps_shifts = eps_shifts;
   h.residual = 1.0;
+  h.seq_base = static_cast<unsigned long long>(++c->epoch) << 32;
   for (int s = 0; s < n_shifts; ++s) h.sigma[s] = sigma ? sigma[s] : 0.0;
   c->ctrl_host[0] = h;
   CU(cudaMemcpyAsync(c->ctrl, c->ctrl_host, sizeof(Ctrl), cudaMemcpyHostToDevice, c->stream));
@@ -928,10 +1043,10 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   auto body = [&](int* l) -> int {
     switch (which) {
       case 0:
-        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, c->gpart, nullptr, c->sms, l));
+        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, c->gpart, nullptr, c->sms, l, nullptr));
         break;
       case 1:
-        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, nullptr, nullptr, c->sms, l));
+        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, nullptr, nullptr, c->sms, l, nullptr));
         break;
       case 9:  // first-generation stencil (+ fused Gram), kept for comparison
         KL(c->ops->dirac_v1(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, c->gpart, nullptr, c->sms, l));
@@ -952,7 +1067,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         break;
       case 3:
         KL(c->ops->axpy_gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, c->gpart, nullptr,
-                             c->sms, l));
+                             c->sms, l, nullptr));
         break;
       case 4:
         KL(c->ops->shift_update(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
@@ -968,7 +1083,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         break;
       case 5:
         KL(c->ops->axpy_gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, nullptr, nullptr,
-                             c->sms, l));
+                             c->sms, l, nullptr));
         break;
       case 6:
         KL(c->ops->rescale_add(c->stream, fptr(c, h[0]), mat(c, M_SCRATCH), fptr(c, h[1]), 1.0, c->V, c->sms, l));

@@ -80,10 +80,49 @@ struct Ctrl {
   double eps;
   double eps_shifts;
   double residual;
+  unsigned long long seq_base;     // sequence number of iteration 0 of this solve in the peer-memory exchange
   int conv[kMaxShifts];            // shift converged in the current iteration
   double resid_shift[kMaxShifts];  // last shifted residual estimate
   double sigma[kMaxShifts];
 };
+
+// ---- peer-memory exchange between the ranks of a slab decomposition (NVLink P2P) -------------
+// Every rank owns a communication buffer that all peers have mapped (CUDA IPC).  A producer
+// writes its contribution straight into the consumers' buffers with ordinary stores, fences at
+// system scope and then publishes a sequence number; the consumer spins on the sequence word in
+// its OWN memory.  Slots are double-buffered by sequence parity; every exchange is a barrier
+// between the ranks, so a producer is never more than one sequence number ahead.
+constexpr int kMaxRanks = 8;
+struct GramPeers {                      // one of the two Gram channels (0: P^dag T, 1: Q^dag Q)
+  cd* slot[kMaxRanks];                  // rank r's block area: [2 parities][nranks][N*N]
+  unsigned long long* seq[kMaxRanks];   // rank r's sequence words: [nranks]
+  int nranks;                           // 0 = no exchange (one rank, or the NCCL path of the primitives)
+  int rank;
+};
+struct HaloPeers {
+  cd* lo_of_right;                      // right neighbour's "from the left" slots: [2 parities][2 sites]
+  cd* hi_of_left;                       // left neighbour's "from the right" slots
+  unsigned long long* seq_lo_of_right;  // sequence word next to each
+  unsigned long long* seq_hi_of_left;
+  const cd* my_lo;                      // this rank's own slots and sequence words
+  const cd* my_hi;
+  const unsigned long long* my_seq_lo;
+  const unsigned long long* my_seq_hi;
+};
+struct GramWait {                       // consumer side of a Gram channel
+  const cd* slots;                      // this rank's block area: [2 parities][nranks][N*N]
+  const unsigned long long* seq;        // this rank's sequence words: [nranks]
+  int nranks;                           // 0 = plain mode (blocks handed over in stream order)
+};
+constexpr long long kSpinTimeoutClocks = 20000000000LL;  // ~10 s: a peer that never arrives is an error, not a hang
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk) ------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

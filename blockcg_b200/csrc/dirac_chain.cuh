@@ -114,31 +114,41 @@ struct GramPart {
 // of kGramGroup consecutive blockIdx, and the group member that finishes LAST adds the group's
 // blocks, in blockIdx order, into one block.  Which member is last varies from run to run, what
 // it computes does not => still bit-reproducible, no floating-point atomics.
-// Buffer layout (complex units of N*N): [0, ngroups) group sums | [kGramRawOff, +grid) raw partial
-// blocks | [kGramCntOff] arrival counters (unsigned, zero at rest: the last member resets its own).
+// Buffer layout (complex units of N*N): [0] final block | [kGramSumOff, +ngroups) group sums |
+// [kGramRawOff, +grid) raw partial blocks | [kGramCntOff] arrival counters (unsigned, zero at rest:
+// whoever completes a count resets it).
 constexpr int kGramGroup = 8;
+constexpr int kGramSumOff = 8;
 constexpr int kGramRawOff = 1024;
 constexpr int kGramCntOff = 3072;
+// Third level, same pattern: the CTA that completes the LAST group adds the group sums in group
+// order into the final block gbuf[0] -- and, in a slab decomposition, stores that block straight
+// into every peer's communication buffer over NVLink and publishes the sequence number of the
+// iteration: the all-"reduce" of the Gram matrix is the tail of the kernel that produced it
+// (each rank then adds the nranks blocks in rank order inside its coefficient kernel, so all
+// ranks get bit-identical matrices and stay in lock-step without a broadcast).
 // Called by the 4 Gram warps (128 threads, named barrier 1) after each has stored its part of the
-// raw block.
+// raw block.  Counters: [0, 1023) groups, [1023] number of finished groups.
 template <int N>
-__device__ __noinline__ void gram_group_reduce(cd* __restrict__ gbuf, int gram_warp) {
+__device__ __noinline__ void gram_group_reduce(cd* __restrict__ gbuf, int gram_warp, const GramPeers& peers,
+                                               const Ctrl* __restrict__ ctrl, int channel) {
   constexpr int nn = N * N;
   __threadfence();
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (gram_warp != 0) return;
   const int lane = threadIdx.x & 31;
   const int group = blockIdx.x / kGramGroup;
+  const int ngroups = (static_cast<int>(gridDim.x) + kGramGroup - 1) / kGramGroup;
   const int first = group * kGramGroup;
   const int members = min(kGramGroup, static_cast<int>(gridDim.x) - first);
-  unsigned* cnt = reinterpret_cast<unsigned*>(gbuf + static_cast<size_t>(kGramCntOff) * nn) + group;
+  unsigned* cnt = reinterpret_cast<unsigned*>(gbuf + static_cast<size_t>(kGramCntOff) * nn);
   unsigned old = 0;
-  if (lane == 0) old = atomicAdd(cnt, 1u);
+  if (lane == 0) old = atomicAdd(cnt + group, 1u);
   old = __shfl_sync(0xffffffffu, old, 0);
   if (old != static_cast<unsigned>(members - 1)) return;
   __threadfence();
   const cd* raw = gbuf + (static_cast<size_t>(kGramRawOff) + first) * nn;
-  cd* dst = gbuf + static_cast<size_t>(group) * nn;
+  cd* gsum = gbuf + static_cast<size_t>(kGramSumOff) * nn;
 #pragma unroll 1
   for (int e = lane; e < nn; e += 32) {
     const int i = e % N, j = e / N;
@@ -150,9 +160,42 @@ __device__ __noinline__ void gram_group_reduce(cd* __restrict__ gbuf, int gram_w
     cd sum = v[0];
 #pragma unroll
     for (int m = 1; m < kGramGroup; ++m) sum = cadd(sum, v[m]);  // absent members contribute +0
-    dst[e] = sum;
+    gsum[static_cast<size_t>(group) * nn + e] = sum;
   }
-  if (lane == 0) *cnt = 0u;
+  if (lane == 0) cnt[group] = 0u;
+  // ---- last group? ----
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) old = atomicAdd(cnt + 1023, 1u);
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old != static_cast<unsigned>(ngroups - 1)) return;
+  __threadfence();
+  const unsigned long long k =
+      (ctrl != nullptr) ? ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter + (channel == 0 ? 1 : 0)) : 0ull;
+  const int np = (ctrl != nullptr) ? peers.nranks : 0;
+#pragma unroll 1
+  for (int e = lane; e < nn; e += 32) {
+    const int i = e % N, j = e / N;
+    if (i < j) continue;
+    double re = 0.0, im = 0.0;
+#pragma unroll 4
+    for (int g = 0; g < ngroups; ++g) {
+      const cd v = __ldcg(reinterpret_cast<const double2*>(gsum + static_cast<size_t>(g) * nn + e));
+      re += v.x;
+      im += v.y;
+    }
+    const cd sum = cmake(re, im);
+    gbuf[e] = sum;
+#pragma unroll 1
+    for (int r = 0; r < np; ++r)
+      peers.slot[r][(static_cast<size_t>(k & 1ull) * np + peers.rank) * nn + e] = sum;
+  }
+  if (lane == 0) cnt[1023] = 0u;
+  if (np > 0) {
+    __threadfence_system();
+    __syncwarp();
+    if (lane < np) st_release_sys(peers.seq[lane] + peers.rank, k);
+  }
 }
 
 template <int N, int G, int K, int W>
@@ -190,7 +233,7 @@ __global__ void __launch_bounds__(ChainGeom<N, G, K, W>::NT, 1)
 dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmU, const cd* __restrict__ in,
                    const cd* __restrict__ U, long long V, long long L, double m2, double sigma,
-                   cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl) {
+                   cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl, const GramPeers peers) {
   using Geo = ChainGeom<N, G, K, W>;
   constexpr int R = Geo::R, SITE = Geo::SITE, PP = Geo::PP, PU = Geo::PU;
   constexpr int SP = Geo::SP, SU = Geo::SU, SO = Geo::SO;
@@ -290,7 +333,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       // scratch: a P ring slot the last tile does not use (slot (T-1) % SP is still being read)
       part.store(gpart + (static_cast<size_t>(kGramRawOff) + blockIdx.x) * N * N,
                  sP + ((T + (warp - Geo::NSW)) % SP) * (K * PP));
-      gram_group_reduce<N>(gpart, warp - Geo::NSW);
+      gram_group_reduce<N>(gpart, warp - Geo::NSW, peers, ctrl, 0);
     };
     switch (warp - Geo::NSW) {
       case 0: { GramPart<N, 0> part; gram_loop(part); break; }

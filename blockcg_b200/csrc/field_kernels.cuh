@@ -857,6 +857,59 @@ static __global__ void halo_wrap_kernel(cd* __restrict__ f, long long V, int sit
   }
 }
 
+// Halo exchange of a slab decomposition over peer memory.  Sequence number of the exchange
+// that follows iteration i: seq_base + i (i = 0: the refresh before the loop).
+static __global__ void halo_push_kernel(const cd* __restrict__ f, long long V, int site, HaloPeers hp,
+                                        const Ctrl* __restrict__ ctrl) {
+  if (ctrl->done) return;
+  const unsigned long long k = ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter);
+  const int n = 2 * site;
+  cd* to_left = hp.hi_of_left + (k & 1ull) * n;    // my sites 0,1    -> left neighbour's slots V, V+1
+  cd* to_right = hp.lo_of_right + (k & 1ull) * n;  // my sites V-2,V-1 -> right neighbour's slots -2,-1
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    to_left[i] = f[i];
+    to_right[i] = f[(V - 2) * site + i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release_sys(hp.seq_hi_of_left, k);
+    st_release_sys(hp.seq_lo_of_right, k);
+  }
+}
+static __global__ void halo_wait_unpack_kernel(cd* __restrict__ f, long long V, int site, HaloPeers hp,
+                                               Ctrl* __restrict__ ctrl) {
+  if (ctrl->done) return;
+  const unsigned long long k = ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter);
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const unsigned long long* w = threadIdx.x ? hp.my_seq_hi : hp.my_seq_lo;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(w) < k)
+      if (clock64() - t0 > kSpinTimeoutClocks) {
+        timed_out = 1;
+        break;
+      }
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (threadIdx.x == 0) {
+      ctrl->status = 4;
+      ctrl->done = 1;
+    }
+    return;
+  }
+  const int n = 2 * site;
+  const cd* lo = hp.my_lo + (k & 1ull) * n;
+  const cd* hi = hp.my_hi + (k & 1ull) * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    f[i - n] = __ldcg(reinterpret_cast<const double2*>(lo + i));                  // slots -2, -1
+    f[V * site + i] = __ldcg(reinterpret_cast<const double2*>(hi + i));          // slots V, V+1
+  }
+}
+
 // pack the two boundary slabs (first 2 / last 2 sites) for a neighbour exchange
 static __global__ void halo_pack_kernel(const cd* __restrict__ f, long long V, int site, cd* __restrict__ send_lo,
                                  cd* __restrict__ send_hi) {

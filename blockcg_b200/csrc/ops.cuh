@@ -1,5 +1,6 @@
 // Host-side launchers, one table per compiled N (see inst.cu / registry in capi.cu).
 #pragma once
+#include <cstring>
 #include "common.cuh"
 #include "field_kernels.cuh"
 #include "dirac_chain.cuh"
@@ -14,15 +15,17 @@ struct OpsTable {
   int fused_gram;  // 1 if the Gram epilogue is fused into K1/K3 at this N
   // Each launcher returns the number of partial Gram blocks it produced (0 if none),
   // or a negative cudaError_t.
+  // peers: peer-memory targets of the fused Gram exchange (nullptr = none)
   int (*dirac)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
-               cd* gpart, const Ctrl* ctrl, int sms, int* launches);
+               cd* gpart, const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers);
   // first-generation tile kernel (intermediate staged in shared memory), kept for comparison
   int (*dirac_v1)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
                   cd* gpart, const Ctrl* ctrl, int sms, int* launches);
   int (*gram)(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
               int* launches);
   int (*axpy_gram)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
-                   const Ctrl* ctrl, int sms, int* launches);
+                   const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers);
+  int fused_exchange;  // 1 if dirac / axpy_gram push the final Gram block to the peers themselves
   int (*axpy_gram_v1)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
                       const Ctrl* ctrl, int sms, int* launches);
   int (*rescale_add)(cudaStream_t st, cd* dst, const cd* L, const cd* src, double r, long long V, int sms,
@@ -218,7 +221,9 @@ struct Ops {
   }
 
   static int dirac(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
-                   cd* gpart, const Ctrl* ctrl, int sms, int* launches) {
+                   cd* gpart, const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers) {
+    GramPeers pe;
+    if (peers) pe = *peers; else std::memset(&pe, 0, sizeof pe);
     if constexpr (CHAIN) {
       prepare(sms);
       const ChainPlan pl = chain_plan(V, sms);
@@ -229,13 +234,13 @@ struct Ops {
       if (e) return e;
       if (gpart != nullptr)
         dirac_chain_kernel<N, CG_, CK, CW, true><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
-            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl);
+            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
       else
         dirac_chain_kernel<N, CG_, CK, CW, false><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
-            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl);
+            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl, pe);
       if (launches) ++*launches;
       e = err();
-      return e ? e : (gpart != nullptr ? (pl.grid + kGramGroup - 1) / kGramGroup : 0);
+      return e ? e : (gpart != nullptr ? 1 : 0);  // the kernel leaves the fully reduced block in gpart[0]
     }
     return dirac_v1(st, in, out, U, V, m2, sigma, gpart, ctrl, sms, launches);
   }
@@ -263,7 +268,9 @@ struct Ops {
   }
 
   static int axpy_gram(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
-                       const Ctrl* ctrl, int sms, int* launches) {
+                       const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers) {
+    GramPeers pe;
+    if (peers) pe = *peers; else std::memset(&pe, 0, sizeof pe);
     if constexpr (APIPE) {
       prepare(sms);
       alignas(64) CUtensorMap tmQ, tmT;
@@ -272,12 +279,12 @@ struct Ops {
       if (e) return e;
       const int grid = clamp_grid((V + APIPE_TS - 1) / APIPE_TS, sms);
       if (gpart != nullptr)
-        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, gpart, ctrl);
+        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, gpart, ctrl, pe);
       else
-        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, nullptr, ctrl);
+        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, nullptr, ctrl, pe);
       if (launches) ++*launches;
       e = err();
-      return e ? e : (gpart != nullptr ? (grid + kGramGroup - 1) / kGramGroup : 0);
+      return e ? e : (gpart != nullptr ? 1 : 0);
     }
     return axpy_gram_v1(st, Q, T, M, V, gpart, ctrl, sms, launches);
   }
@@ -358,7 +365,7 @@ struct Ops {
   }
 
   // see gram_group_reduce() for the layout of the partial-Gram buffer
-  static int max_partials(int sms) { return (32 * sms > kGramCntOff + 8) ? 32 * sms : kGramCntOff + 8; }
+  static int max_partials(int sms) { return (32 * sms > kGramCntOff + 32) ? 32 * sms : kGramCntOff + 32; }
 };
 
 template <int N>
@@ -371,6 +378,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::dirac_v1,
                              &Ops<N>::gram,
                              &Ops<N>::axpy_gram,
+                             (Ops<N>::CHAIN && Ops<N>::APIPE) ? 1 : 0,
                              &Ops<N>::axpy_gram_v1,
                              &Ops<N>::rescale_add,
                              &Ops<N>::trsm,

@@ -461,6 +461,36 @@ struct SmallSmem {
   }
 };
 
+// Slab decomposition: wait until every rank's block with sequence number k has landed in this
+// rank's communication buffer, then point (src, nsrc) at the nranks blocks (summed in rank order
+// by sm_reduce_gram: every rank computes the bit-identical matrix).  Returns false on time-out.
+__device__ __forceinline__ bool sm_wait_peers(const GramWait& w, unsigned long long k, int nn, const cd*& src,
+                                              int& nsrc, Ctrl* ctrl) {
+  if (w.nranks == 0) return true;
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < w.nranks) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(w.seq + threadIdx.x) < k)
+      if (clock64() - t0 > kSpinTimeoutClocks) {
+        timed_out = 1;
+        break;
+      }
+  }
+  __syncthreads();
+  if (timed_out) {
+    if (threadIdx.x == 0) {
+      ctrl->status = 4;
+      ctrl->done = 1;
+    }
+    return false;
+  }
+  src = w.slots + static_cast<size_t>(k & 1ull) * w.nranks * nn;
+  nsrc = w.nranks;
+  return true;
+}
+
 // ---- stand-alone helpers used by the primitives (bcg_gram, bcg_thinqr) -------------------
 // out = reduced Gram
 __global__ void __launch_bounds__(kSmallThreads)
@@ -524,7 +554,7 @@ rq_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm, 
 // Also: iteration bookkeeping (iter++, promote stop -> done, retire converged shifts).
 __global__ void __launch_bounds__(kSmallThreads)
 rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpart, int nparts,
-                 Ctrl* __restrict__ ctrl) {
+                 Ctrl* __restrict__ ctrl, const GramWait gw) {
   if (ctrl->done) return;
   if (ctrl->stop) {
     __syncthreads();
@@ -561,7 +591,10 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   long long tt[6];
   tt[0] = clock64();
 #endif
-  sm_reduce_gram(Ainv, gpart, nparts, N, s.mat[4]);
+  const cd* gsrc = gpart;
+  int nsrc = nparts;
+  if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
+  sm_reduce_gram(Ainv, gsrc, nsrc, N, s.mat[4]);
 #ifdef BCG_DEBUG_TIMING
   tt[1] = clock64();
 #endif
@@ -602,7 +635,7 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
 //               (block_solvers.hpp:163-181)
 __global__ void __launch_bounds__(kSmallThreads)
 rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ b_norm,
-                 const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl) {
+                 const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl, const GramWait gw) {
   if (ctrl->done) return;
   const int sh = blockIdx.x;
   if (sh >= ctrl->n_unconv) return;
@@ -615,7 +648,10 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   cd* G = s.mat[0];
   cd* rho = s.mat[1];
   cd* t0 = s.mat[2];
-  sm_reduce_gram(G, gpart, nparts, N, s.mat[4]);
+  const cd* gsrc = gpart;
+  int nsrc = nparts;
+  if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
+  sm_reduce_gram(G, gsrc, nsrc, N, s.mat[4]);
   const int info = sm_chol_upper(rho, G, t0, N, s.info);
   cd* rho_g = mats + L.fixed((iter & 1) ? M_RHO1 : M_RHO0);
   const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
@@ -730,7 +766,7 @@ bcg_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm,
 // A-step: alpha = LU(P^dag T).solve(r2) ; -alpha ; A_0 = alpha
 __global__ void __launch_bounds__(kSmallThreads)
 bcg_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpart, int nparts,
-                  Ctrl* __restrict__ ctrl) {
+                  Ctrl* __restrict__ ctrl, const GramWait gw) {
   if (ctrl->done) return;
   if (ctrl->stop) {
     __syncthreads();
@@ -745,7 +781,10 @@ bcg_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpa
   const int iter = ctrl->iter + 1;
   __syncthreads();
   if (threadIdx.x == 0) ctrl->iter = iter;
-  sm_reduce_gram(s.mat[0], gpart, nparts, N, s.mat[4]);
+  const cd* gsrc = gpart;
+  int nsrc = nparts;
+  if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
+  sm_reduce_gram(s.mat[0], gsrc, nsrc, N, s.mat[4]);
   sm_copy(s.mat[1], mats + L.fixed(M_R2), nn);  // X enters as B = r2
   sm_lu_solve(s.mat[1], s.mat[0], s.lw, N);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
@@ -758,7 +797,7 @@ bcg_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpa
 // B-step: r2_old = r2 ; r2 = R^dag R ; beta = LU(r2_old).solve(r2) ; residual ; B_0 = beta
 __global__ void __launch_bounds__(kSmallThreads)
 bcg_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ b_norm,
-                  const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl) {
+                  const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl, const GramWait gw) {
   if (ctrl->done) return;
   extern __shared__ __align__(16) unsigned char raw[];
   const int N = L.N, nn = N * N;
@@ -768,7 +807,10 @@ bcg_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__
   cd* r2 = s.mat[0];
   cd* r2old = s.mat[1];
   cd* beta = s.mat[2];
-  sm_reduce_gram(r2, gpart, nparts, N, s.mat[4]);
+  const cd* gsrc = gpart;
+  int nsrc = nparts;
+  if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter), nn, gsrc, nsrc, ctrl)) return;
+  sm_reduce_gram(r2, gsrc, nsrc, N, s.mat[4]);
   sm_copy(r2old, mats + L.fixed(M_R2), nn);
   sm_copy(beta, r2, nn);
   sm_lu_solve(beta, r2old, s.lw, N);

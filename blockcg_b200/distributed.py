@@ -7,7 +7,7 @@ communicator and stream (blockcg_b200/csrc/capi.cu: halo_refresh, gram_finalize)
 """
 import numpy as np
 
-from .capi import UNIQUE_ID_BYTES, Context
+from .capi import IPC_HANDLE_BYTES, UNIQUE_ID_BYTES, Context
 
 HALO = 2  # op = m^2 - D^2 reaches x +- 2 (inc/dirac_op.hpp:14-21,36-43)
 
@@ -44,7 +44,21 @@ def broadcast_unique_id(dist, device=None):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def make_context(dist, V, N, max_shifts, device, U_global, mass):
+def exchange_ipc_handles(dist, ctx, device=None):
+    """Map every rank's communication buffer into every other rank (CUDA IPC, one node): after
+    this the iteration loop exchanges halos and Gram blocks with P2P stores over NVLink and
+    contains no NCCL call."""
+    import torch
+    mine = torch.frombuffer(bytearray(ctx.ipc_handle()), dtype=torch.uint8).clone()
+    if device is not None:
+        mine = mine.to(device)
+    allh = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(allh, mine)
+    ctx.ipc_open(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+    dist.barrier()  # nobody pushes before everybody has mapped everybody
+
+
+def make_context(dist, V, N, max_shifts, device, U_global, mass, p2p=True):
     """Slab context of this rank, communicator initialised, links (own slab) uploaded."""
     rank, world = dist.get_rank(), dist.get_world_size()
     b, e = slab_range(V, rank, world)
@@ -52,5 +66,7 @@ def make_context(dist, V, N, max_shifts, device, U_global, mass):
     import torch
     uid = broadcast_unique_id(dist, torch.device("cuda", device) if dist.get_backend() == "nccl" else None)
     ctx.comm_init(uid)
+    if p2p and world > 1 and dist.get_backend() == "nccl":
+        exchange_ipc_handles(dist, ctx, torch.device("cuda", device))
     ctx.set_links(np.ascontiguousarray(U_global[b:e]), mass)
     return ctx, (b, e)

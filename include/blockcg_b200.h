@@ -51,6 +51,7 @@ typedef enum {
 
 #define BCG_MAX_SHIFTS 32
 #define BCG_UNIQUE_ID_BYTES 128
+#define BCG_IPC_HANDLE_BYTES 64
 
 /* ---- library / build info -------------------------------------------------------- */
 const char* bcg_version(void);
@@ -73,6 +74,13 @@ const char* bcg_last_error(const bcg_ctx* ctx);
  * torch.distributed / MPI), every rank calls bcg_comm_init. */
 int bcg_comm_get_unique_id(void* id_out /* BCG_UNIQUE_ID_BYTES */);
 int bcg_comm_init(bcg_ctx* ctx, const void* id /* BCG_UNIQUE_ID_BYTES */);
+/* Peer-memory exchange over NVLink (optional, one process per GPU on one node): every rank
+ * obtains the CUDA-IPC handle of its communication buffer, the host gathers the handles of
+ * all ranks (rank order) and hands the array to every rank, then synchronises the ranks
+ * once.  With it the iteration loop contains no NCCL call: the Gram kernels store their
+ * N x N block into every peer's buffer themselves, the halo sites travel as P2P stores. */
+int bcg_comm_ipc_handle(bcg_ctx* ctx, void* handle_out /* BCG_IPC_HANDLE_BYTES */);
+int bcg_comm_ipc_open(bcg_ctx* ctx, const void* handles /* nranks * BCG_IPC_HANDLE_BYTES */);
 
 /* ---- operator --------------------------------------------------------------------- */
 /* links_host: this rank's [v_local][3][3] links; halos (2 sites each side) are

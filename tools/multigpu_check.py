@@ -25,8 +25,9 @@ def main():
     V, N, mass = 4096, 12, 0.05
     shifts = [0.0, 1e-4, 1e-2, 1e-1]
     U, B = o.make_inputs(V, N, 1)
-    ctx, (b, e) = D.make_context(dist, V, N, len(shifts), local, U, mass)
-    res = {"world": world, "V": V, "N": N}
+    p2p = os.environ.get("BCG_NO_P2P", "0") != "1"
+    ctx, (b, e) = D.make_context(dist, V, N, len(shifts), local, U, mass, p2p=p2p)
+    res = {"world": world, "V": V, "N": N, "p2p": p2p}
     hb, ha = ctx.field(np.ascontiguousarray(B[b:e])), ctx.field()
     G = ctx.op(ha, hb, sigma=0.125, want_gram=True)
     AB = o.op(U, B, mass, 0.125)
