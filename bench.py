@@ -33,6 +33,9 @@ import time
 
 import numpy as np
 
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
+os.environ["NCCL_DEBUG"] = os.environ.get("BCG_NCCL_DEBUG", "WARN")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

@@ -133,56 +133,66 @@ template <int N>
 __device__ __noinline__ void gram_group_reduce(cd* __restrict__ gbuf, int gram_warp, const GramPeers& peers,
                                                const Ctrl* __restrict__ ctrl, int channel) {
   constexpr int nn = N * N;
-  __threadfence();
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (gram_warp != 0) return;
-  const int lane = threadIdx.x & 31;
+  __shared__ unsigned s_old;
+  const int t = gram_warp * 32 + (threadIdx.x & 31);  // 0 .. 127
   const int group = blockIdx.x / kGramGroup;
   const int ngroups = (static_cast<int>(gridDim.x) + kGramGroup - 1) / kGramGroup;
   const int first = group * kGramGroup;
   const int members = min(kGramGroup, static_cast<int>(gridDim.x) - first);
   unsigned* cnt = reinterpret_cast<unsigned*>(gbuf + static_cast<size_t>(kGramCntOff) * nn);
-  unsigned old = 0;
-  if (lane == 0) old = atomicAdd(cnt + group, 1u);
-  old = __shfl_sync(0xffffffffu, old, 0);
-  if (old != static_cast<unsigned>(members - 1)) return;
   __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (t == 0) s_old = atomicAdd(cnt + group, 1u);
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (s_old != static_cast<unsigned>(members - 1)) return;
+  __threadfence();
+  // ---- this CTA completed its group: add the group's raw blocks in blockIdx order ----
   const cd* raw = gbuf + (static_cast<size_t>(kGramRawOff) + first) * nn;
   cd* gsum = gbuf + static_cast<size_t>(kGramSumOff) * nn;
 #pragma unroll 1
-  for (int e = lane; e < nn; e += 32) {
+  for (int e = t; e < nn; e += 128) {
     const int i = e % N, j = e / N;
     if (i < j) continue;  // only the lower triangle is produced and consumed
     cd v[kGramGroup];
 #pragma unroll
-    for (int m = 0; m < kGramGroup; ++m)
+    for (int m = 0; m < kGramGroup; ++m)  // all loads in flight, then a fixed-order sum
       v[m] = (m < members) ? __ldcg(reinterpret_cast<const double2*>(raw + static_cast<size_t>(m) * nn + e)) : czero();
     cd sum = v[0];
 #pragma unroll
     for (int m = 1; m < kGramGroup; ++m) sum = cadd(sum, v[m]);  // absent members contribute +0
     gsum[static_cast<size_t>(group) * nn + e] = sum;
   }
-  if (lane == 0) cnt[group] = 0u;
-  // ---- last group? ----
   __threadfence();
-  __syncwarp();
-  if (lane == 0) old = atomicAdd(cnt + 1023, 1u);
-  old = __shfl_sync(0xffffffffu, old, 0);
-  if (old != static_cast<unsigned>(ngroups - 1)) return;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (t == 0) {
+    cnt[group] = 0u;
+    s_old = atomicAdd(cnt + 1023, 1u);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (s_old != static_cast<unsigned>(ngroups - 1)) return;
   __threadfence();
+  // ---- ... and the last group: add the group sums in group order, publish ----
   const unsigned long long k =
       (ctrl != nullptr) ? ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter + (channel == 0 ? 1 : 0)) : 0ull;
   const int np = (ctrl != nullptr) ? peers.nranks : 0;
+  constexpr int CH = 20;  // group sums fetched per round (148 SMs / 8 = 19 groups: one round)
 #pragma unroll 1
-  for (int e = lane; e < nn; e += 32) {
+  for (int e = t; e < nn; e += 128) {
     const int i = e % N, j = e / N;
     if (i < j) continue;
     double re = 0.0, im = 0.0;
-#pragma unroll 4
-    for (int g = 0; g < ngroups; ++g) {
-      const cd v = __ldcg(reinterpret_cast<const double2*>(gsum + static_cast<size_t>(g) * nn + e));
-      re += v.x;
-      im += v.y;
+#pragma unroll 1
+    for (int g0 = 0; g0 < ngroups; g0 += CH) {
+      cd v[CH];
+#pragma unroll
+      for (int g = 0; g < CH; ++g)
+        v[g] = (g0 + g < ngroups) ? __ldcg(reinterpret_cast<const double2*>(gsum + static_cast<size_t>(g0 + g) * nn + e))
+                                  : czero();
+#pragma unroll
+      for (int g = 0; g < CH; ++g) {
+        re += v[g].x;
+        im += v[g].y;
+      }
     }
     const cd sum = cmake(re, im);
     gbuf[e] = sum;
@@ -190,11 +200,11 @@ __device__ __noinline__ void gram_group_reduce(cd* __restrict__ gbuf, int gram_w
     for (int r = 0; r < np; ++r)
       peers.slot[r][(static_cast<size_t>(k & 1ull) * np + peers.rank) * nn + e] = sum;
   }
-  if (lane == 0) cnt[1023] = 0u;
+  if (t == 0) cnt[1023] = 0u;
   if (np > 0) {
     __threadfence_system();
-    __syncwarp();
-    if (lane < np) st_release_sys(peers.seq[lane] + peers.rank, k);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (t < np) st_release_sys(peers.seq[t] + peers.rank, k);
   }
 }
 
