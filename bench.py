@@ -33,8 +33,10 @@ import time
 
 import numpy as np
 
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
-os.environ["NCCL_DEBUG"] = os.environ.get("BCG_NCCL_DEBUG", "WARN")
+# stdout carries the ONE JSON line and nothing else: libraries that chat on file descriptor 1 (NCCL prints its
+# version banner there) are sent to stderr, the JSON line goes to a private copy of the original stdout
+JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -154,7 +156,7 @@ def run_reference(args, w, wname):
             "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "extrapolated": True, "s_per_iteration": s_per_iter}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 def config_of(wname, w, gpus):
@@ -312,7 +314,7 @@ def run_ours(args, w, wname):
                          "frac_of_hbm_peak_with_gram": dirac["frac"], "ms_with_gram": dirac["ms"],
                          "alg_bytes": dirac["alg_bytes"]},
             "kernels": kern, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     if world == 1 and args.record_iterations:
         os.makedirs(os.path.dirname(ITER_FILE), exist_ok=True)
         d = {}
