@@ -25,7 +25,7 @@ STATUS = {0: "BCG_OK", 1: "BCG_ERR_INVALID", 2: "BCG_ERR_CUDA", 3: "BCG_ERR_NOT_
 # every symbol include/blockcg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "bcg_version", "bcg_supports_nrhs", "bcg_ctx_create", "bcg_ctx_destroy", "bcg_last_error",
-    "bcg_comm_get_unique_id", "bcg_comm_init", "bcg_comm_ipc_handle", "bcg_comm_ipc_open", "bcg_set_links", "bcg_field_alloc", "bcg_field_free",
+    "bcg_ctx_create_4d", "bcg_set_links_4d", "bcg_comm_get_unique_id", "bcg_comm_init", "bcg_comm_ipc_handle", "bcg_comm_ipc_open", "bcg_set_links", "bcg_field_alloc", "bcg_field_free",
     "bcg_field_upload", "bcg_field_download", "bcg_field_zero", "bcg_field_copy", "bcg_op", "bcg_gram",
     "bcg_add", "bcg_add_scalar", "bcg_rescale_add", "bcg_trsm", "bcg_thinqr", "bcg_true_residual",
     "bcg_solve_bcg_dev", "bcg_solve_bcgrq_dev", "bcg_solve_sbcgrq_dev", "bcg_solve_bcg", "bcg_solve_bcgrq",
@@ -72,6 +72,9 @@ def load():
     lib.bcg_comm_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
     lib.bcg_comm_ipc_open.argtypes = [C.c_void_p, C.c_void_p]
     lib.bcg_set_links.argtypes = [C.c_void_p, _dp, C.c_double]
+    lib.bcg_set_links_4d.argtypes = [C.c_void_p, _dp, C.c_double]
+    lib.bcg_ctx_create_4d.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int]
     lib.bcg_field_alloc.argtypes = [C.c_void_p, _ip]
     lib.bcg_field_free.argtypes = [C.c_void_p, C.c_int]
     lib.bcg_field_upload.argtypes = [C.c_void_p, C.c_int, _dp]
@@ -116,12 +119,21 @@ def mat_from_cm(buf, N):
 class Context:
     """One GPU, one slab of `v_local` sites, `n_rhs` right-hand sides."""
 
-    def __init__(self, v_local, n_rhs, max_shifts=1, device=0, rank=0, nranks=1):
+    def __init__(self, v_local, n_rhs, max_shifts=1, device=0, rank=0, nranks=1, dims=None):
+        """dims = (L0, L1, L2, L3_local): a context of the 4-D extension of the operator (v_local is
+        then ignored and set to the product); default: the reference's 1-D chain of v_local sites."""
         self.lib = load()
+        self.dims = tuple(int(d) for d in dims) if dims is not None else None
+        if self.dims is not None:
+            v_local = int(np.prod(self.dims))
         self.V, self.N, self.S = int(v_local), int(n_rhs), int(max_shifts)
         self.rank, self.nranks = rank, nranks
         self._h = C.c_void_p()
-        rc = self.lib.bcg_ctx_create(C.byref(self._h), self.V, self.N, self.S, device, rank, nranks)
+        if self.dims is not None:
+            rc = self.lib.bcg_ctx_create_4d(C.byref(self._h), (C.c_int64 * 4)(*self.dims), self.N, self.S, device,
+                                            rank, nranks)
+        else:
+            rc = self.lib.bcg_ctx_create(C.byref(self._h), self.V, self.N, self.S, device, rank, nranks)
         if rc:
             msg = self.lib.bcg_last_error(self._h).decode() if self._h else "context creation failed"
             self.lib.bcg_ctx_destroy(self._h)
@@ -176,6 +188,10 @@ class Context:
     # ---- operator / fields ----
     def set_links(self, U, mass):
         U = np.ascontiguousarray(U, dtype=np.complex128)
+        if self.dims is not None:
+            assert U.shape == (self.V, 4, 3, 3), U.shape
+            self._ck(self.lib.bcg_set_links_4d(self._h, _dptr(U), float(mass)))
+            return
         assert U.shape == (self.V, 3, 3), U.shape
         self._ck(self.lib.bcg_set_links(self._h, _dptr(U), float(mass)))
 

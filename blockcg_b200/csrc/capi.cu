@@ -105,7 +105,12 @@ struct GraphCache {
 struct bcg_ctx {
   int device = 0, rank = 0, nranks = 1;
   long long V = 0;
-  long long cap = 0;  // allocated sites after site 0 (>= V + 2), see OpsTable::field_capacity
+  long long cap = 0;  // allocated sites after site 0 (>= V + halo), see OpsTable::field_capacity
+  int ndim = 1;       // 1: the reference's chain ; 4: the 4-D extension (dirac4d.cuh)
+  Lattice4 lat{};     // local extents of the 4-D lattice
+  long long halo = 2; // halo sites on either side of every field: 2 (chain) or one x3-slice (4-D)
+  int links_site = 9; // complex numbers of link data per site: 9 or 36
+  int work_D = -1;    // 4-D: intermediate field D P
   int N = 0, S = 1, sms = 0;
   double mass = 0.0;
   bool links_set = false;
@@ -175,9 +180,9 @@ int fail(bcg_ctx* c, int code, const char* fmt, ...) {
   } while (0)
 
 inline size_t site_elems(const bcg_ctx* c) { return static_cast<size_t>(3) * c->N; }
-inline size_t field_elems(const bcg_ctx* c) { return static_cast<size_t>(c->cap + 2) * site_elems(c); }
-inline cd* fptr(const bcg_ctx* c, int h) { return c->fields[h] + 2 * site_elems(c); }
-inline cd* uptr(const bcg_ctx* c) { return c->U_alloc + 2 * 9; }
+inline size_t field_elems(const bcg_ctx* c) { return static_cast<size_t>(c->cap + c->halo) * site_elems(c); }
+inline cd* fptr(const bcg_ctx* c, int h) { return c->fields[h] + c->halo * site_elems(c); }
+inline cd* uptr(const bcg_ctx* c) { return c->U_alloc + c->halo * c->links_site; }
 inline bool valid(const bcg_ctx* c, int h) {
   return h >= 0 && h < static_cast<int>(c->fields.size()) && c->fields[h] != nullptr;
 }
@@ -253,14 +258,15 @@ int field_alloc(bcg_ctx* c, int* h) {
 // Fill the 2+2 halo sites of a field (site = 3N) or of the links (site = 9).
 int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
   if (c->nranks == 1) {
-    const int n = 4 * site;
-    halo_wrap_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(f, c->V, site, ctrl);
+    const long long n = 2 * c->halo * site;
+    const unsigned blocks = static_cast<unsigned>(n / 256 + 1 < 2048 ? n / 256 + 1 : 2048);
+    halo_wrap_kernel<<<blocks, 256, 0, c->stream>>>(f, c->V, site, c->halo, ctrl);
     if (launches) ++*launches;
     CU(cudaGetLastError());
     return BCG_OK;
   }
-  if (c->V < 2) return fail(c, BCG_ERR_INVALID, "slab decomposition needs >= 2 sites per rank");
-  if (c->p2p_ready && ctrl != nullptr && site == 3 * c->N) {
+  if (c->V < c->halo) return fail(c, BCG_ERR_INVALID, "slab decomposition needs >= %lld sites per rank", c->halo);
+  if (c->ndim == 1 && c->p2p_ready && ctrl != nullptr && site == 3 * c->N) {
     // inside the iteration loop: boundary sites go straight into the neighbours' buffers over
     // NVLink (P2P stores + sequence word), the receiver copies them into its halo slots
     const HaloPeers hp = halo_peers(c);
@@ -272,14 +278,15 @@ int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
   }
   if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
   const int left = (c->rank + c->nranks - 1) % c->nranks, right = (c->rank + 1) % c->nranks;
-  const size_t cnt = static_cast<size_t>(2) * site * 2;  // doubles
-  // boundary sites are contiguous in the field and halo slots are contiguous too:
-  // no pack/unpack kernels, NCCL moves them directly over NVLink.
+  const long long H = c->halo;
+  const size_t cnt = static_cast<size_t>(H) * site * 2;  // doubles
+  // boundary sites are contiguous in the field and halo slots are contiguous too (for the 4-D
+  // lattice a whole x3-slice): no pack/unpack kernels, NCCL moves them directly over NVLink.
   NC(ncclGroupStart());
-  NC(ncclSend(f, cnt, ncclDouble, left, c->comm, c->stream));                                   // sites 0,1
-  NC(ncclSend(f + (c->V - 2) * site, cnt, ncclDouble, right, c->comm, c->stream));              // sites V-2,V-1
-  NC(ncclRecv(f + c->V * site, cnt, ncclDouble, right, c->comm, c->stream));                    // slots V,V+1
-  NC(ncclRecv(f - 2 * static_cast<long long>(site), cnt, ncclDouble, left, c->comm, c->stream));  // slots -2,-1
+  NC(ncclSend(f, cnt, ncclDouble, left, c->comm, c->stream));                        // first H sites
+  NC(ncclSend(f + (c->V - H) * site, cnt, ncclDouble, right, c->comm, c->stream));   // last H sites
+  NC(ncclRecv(f + c->V * site, cnt, ncclDouble, right, c->comm, c->stream));         // slots V .. V+H-1
+  NC(ncclRecv(f - H * site, cnt, ncclDouble, left, c->comm, c->stream));             // slots -H .. -1
   NC(ncclGroupEnd());
   return BCG_OK;
 }
@@ -316,6 +323,38 @@ int gram_to_gred(bcg_ctx* c, const cd* a, const cd* b, int* launches) {
   if (c->nranks > 1) {
     if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
     NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
+  }
+  return BCG_OK;
+}
+
+// out = (m^2 + sigma) in - D(D in), optionally with the partial Gram in^dag out in c->gpart.
+// `in` must have a valid halo.  Returns the number of partial Gram blocks (0 if none) or < 0.
+// 1-D chain: one fused kernel.  4-D: two sweeps through the intermediate field (whose halo is
+// refreshed in between) and the stand-alone Gram kernel.
+int apply_op(bcg_ctx* c, cd* in, cd* out, double sigma, bool want_gram, const Ctrl* ctrl, int* launches,
+             const GramPeers* peers, int* np_out) {
+  const double m2 = c->mass * c->mass;
+  if (c->ndim == 1) {
+    int np = c->ops->dirac(c->stream, in, out, uptr(c), c->V, m2, sigma, want_gram ? c->gpart : nullptr, ctrl, c->sms,
+                           launches, peers);
+    KL(np);
+    *np_out = np;
+    return BCG_OK;
+  }
+  if (c->work_D < 0) {
+    int r = field_alloc(c, &c->work_D);
+    if (r) return r;
+  }
+  cd* tmp = fptr(c, c->work_D);
+  KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, c->V, m2, sigma, 0, ctrl, launches));
+  int r = halo_refresh(c, tmp, 3 * c->N, ctrl, launches);
+  if (r) return r;
+  KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, c->V, m2, sigma, 1, ctrl, launches));
+  *np_out = 0;
+  if (want_gram) {
+    int np = c->ops->gram(c->stream, in, out, c->V, c->gpart, ctrl, c->sms, launches);
+    KL(np);
+    *np_out = np;
   }
   return BCG_OK;
 }
@@ -363,11 +402,26 @@ const char* bcg_version(void) { return "blockcg_b200 0.1 (sm_100a)"; }
 int bcg_supports_nrhs(int n) { return get_ops(n) != nullptr; }
 const char* bcg_last_error(const bcg_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
-int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, int device, int rank, int nranks) {
+static int ctx_create(bcg_ctx** out, int64_t v_local, const int64_t* dims, int n_rhs, int max_shifts, int device,
+                      int rank, int nranks) {
   if (!out) return BCG_ERR_INVALID;
   *out = nullptr;
   bcg_ctx* c = new bcg_ctx();
   *out = c;  // returned even on failure so the message can be read; destroy() is safe
+  if (dims) {
+    for (int m = 0; m < 4; ++m)
+      if (dims[m] < 1 || dims[m] > (1 << 20)) return fail(c, BCG_ERR_INVALID, "bad lattice extent %lld", (long long)dims[m]);
+    c->ndim = 4;
+    c->lat.L0 = static_cast<int>(dims[0]);
+    c->lat.L1 = static_cast<int>(dims[1]);
+    c->lat.L2 = static_cast<int>(dims[2]);
+    c->lat.L3 = static_cast<int>(dims[3]);
+    c->lat.s2 = dims[0] * dims[1];
+    c->lat.s3 = dims[0] * dims[1] * dims[2];
+    c->halo = c->lat.s3;
+    c->links_site = 36;
+    v_local = c->lat.s3 * dims[3];
+  }
   if (v_local < 1 || max_shifts < 1 || max_shifts > BCG_MAX_SHIFTS || nranks < 1 || rank < 0 || rank >= nranks)
     return fail(c, BCG_ERR_INVALID, "bad argument (v_local=%lld max_shifts=%d rank=%d/%d)", (long long)v_local,
                 max_shifts, rank, nranks);
@@ -391,6 +445,7 @@ int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, in
   c->sms = prop.multiProcessorCount;
   c->ops->prepare(c->sms);
   c->cap = c->ops->field_capacity(c->V, c->sms);
+  if (c->cap < c->V + c->halo) c->cap = c->V + c->halo;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->L.N = n_rhs;
   c->L.S = max_shifts;
@@ -405,8 +460,8 @@ int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, in
   CU(cudaMemset(c->ctrl, 0, sizeof(Ctrl)));
   CU(cudaMallocHost(&c->ctrl_host, 2 * sizeof(Ctrl)));
   CU(cudaMallocHost(&c->mat_host, 4 * c->L.nn() * sizeof(cd)));
-  CU(cudaMalloc(&c->U_alloc, static_cast<size_t>(c->cap + 2) * 9 * sizeof(cd)));
-  CU(cudaMemset(c->U_alloc, 0, static_cast<size_t>(c->cap + 2) * 9 * sizeof(cd)));
+  CU(cudaMalloc(&c->U_alloc, static_cast<size_t>(c->cap + c->halo) * c->links_site * sizeof(cd)));
+  CU(cudaMemset(c->U_alloc, 0, static_cast<size_t>(c->cap + c->halo) * c->links_site * sizeof(cd)));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   for (auto& e : c->ev_batch) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   c->small_smem = SmallSmem::bytes(n_rhs);
@@ -421,6 +476,15 @@ int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, in
     CU(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
   }
   return BCG_OK;
+}
+
+int bcg_ctx_create(bcg_ctx** out, int64_t v_local, int n_rhs, int max_shifts, int device, int rank, int nranks) {
+  return ctx_create(out, v_local, nullptr, n_rhs, max_shifts, device, rank, nranks);
+}
+int bcg_ctx_create_4d(bcg_ctx** out, const int64_t* dims_local, int n_rhs, int max_shifts, int device, int rank,
+                      int nranks) {
+  if (!dims_local) return BCG_ERR_INVALID;
+  return ctx_create(out, 0, dims_local, n_rhs, max_shifts, device, rank, nranks);
 }
 
 int bcg_ctx_destroy(bcg_ctx* c) {
@@ -511,18 +575,22 @@ int bcg_comm_ipc_open(bcg_ctx* c, const void* handles) {
   return BCG_OK;
 }
 
-int bcg_set_links(bcg_ctx* c, const double* links_host, double mass) {
+static int set_links(bcg_ctx* c, const double* links_host, double mass, int ndim) {
   if (!c || !links_host) return fail(c, BCG_ERR_INVALID, "null argument");
+  if (c->ndim != ndim)
+    return fail(c, BCG_ERR_INVALID, "this is a %d-D context: use bcg_set_links%s", c->ndim, c->ndim == 4 ? "_4d" : "");
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(uptr(c), links_host, static_cast<size_t>(c->V) * 9 * sizeof(cd), cudaMemcpyHostToDevice,
-                     c->stream));
-  int r = halo_refresh(c, uptr(c), 9, nullptr, nullptr);
+  CU(cudaMemcpyAsync(uptr(c), links_host, static_cast<size_t>(c->V) * c->links_site * sizeof(cd),
+                     cudaMemcpyHostToDevice, c->stream));
+  int r = halo_refresh(c, uptr(c), c->links_site, nullptr, nullptr);
   if (r) return r;
   CU(cudaStreamSynchronize(c->stream));
   c->mass = mass;
   c->links_set = true;
   return BCG_OK;
 }
+int bcg_set_links(bcg_ctx* c, const double* links_host, double mass) { return set_links(c, links_host, mass, 1); }
+int bcg_set_links_4d(bcg_ctx* c, const double* links_host, double mass) { return set_links(c, links_host, mass, 4); }
 
 int bcg_field_alloc(bcg_ctx* c, int* h) {
   if (!c || !h) return fail(c, BCG_ERR_INVALID, "null argument");
@@ -569,9 +637,9 @@ int bcg_op(bcg_ctx* c, int out, int in, double sigma, double* gram_host) {
   CU(cudaSetDevice(c->device));
   int r = halo_refresh(c, fptr(c, in), 3 * c->N, nullptr, nullptr);
   if (r) return r;
-  int np = c->ops->dirac(c->stream, fptr(c, in), fptr(c, out), uptr(c), c->V, c->mass * c->mass, sigma,
-                         gram_host ? c->gpart : nullptr, nullptr, c->sms, nullptr, nullptr);
-  KL(np);
+  int np = 0;
+  r = apply_op(c, fptr(c, in), fptr(c, out), sigma, gram_host != nullptr, nullptr, nullptr, nullptr, &np);
+  if (r) return r;
   if (gram_host) {
     const size_t nn = c->L.nn();
     gram_reduce_kernel<<<1, kSmallThreads, (1 + kRedSlices) * nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
@@ -661,8 +729,9 @@ int bcg_true_residual(bcg_ctx* c, int x, int b, double sigma, double* res_host) 
   r = halo_refresh(c, fptr(c, x), 3 * c->N, nullptr, nullptr);
   if (r) return r;
   cd* T = fptr(c, c->work_T);
-  KL(c->ops->dirac(c->stream, fptr(c, x), T, uptr(c), c->V, c->mass * c->mass, sigma, nullptr, nullptr, c->sms,
-                   nullptr, nullptr));
+  int np_unused = 0;
+  r = apply_op(c, fptr(c, x), T, sigma, false, nullptr, nullptr, nullptr, &np_unused);
+  if (r) return r;
   const long long n = c->V * static_cast<long long>(site_elems(c));
   sub_kernel<<<c->sms * 8, 256, 0, c->stream>>>(T, T, fptr(c, b), n);
   CU(cudaGetLastError());
@@ -704,13 +773,13 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
   // slab decomposition with mapped peer buffers: the Gram kernels push their block to every
   // rank themselves and the coefficient kernels wait for the sequence words -- no NCCL call,
   // no extra reduction kernel in the loop
-  const bool fused = c->nranks > 1 && c->p2p_ready && c->ops->fused_exchange;
+  const bool fused = c->nranks > 1 && c->p2p_ready && c->ops->fused_exchange && c->ndim == 1;
   const GramPeers gp0 = fused ? gram_peers(c, 0) : GramPeers{}, gp1 = fused ? gram_peers(c, 1) : GramPeers{};
   const GramWait gw0 = fused ? gram_wait(c, 0) : GramWait{}, gw1 = fused ? gram_wait(c, 1) : GramWait{};
-  int np = c->ops->dirac(c->stream, p.P0, p.T, uptr(c), c->V, c->mass * c->mass, p.sigma0, c->gpart, c->ctrl,
-                         c->sms, launches, fused ? &gp0 : nullptr);
-  KL(np);
-  int r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
+  int np = 0;
+  int r = apply_op(c, p.P0, p.T, p.sigma0, true, c->ctrl, launches, fused ? &gp0 : nullptr, &np);
+  if (r) return r;
+  r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
   if (p.kind == 1)
     rq_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
@@ -1042,12 +1111,18 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   }
   auto body = [&](int* l) -> int {
     switch (which) {
-      case 0:
-        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, c->gpart, nullptr, c->sms, l, nullptr));
+      case 0: {
+        int np_ = 0;
+        int r_ = apply_op(c, fptr(c, h[0]), fptr(c, h[1]), 0.0, true, nullptr, l, nullptr, &np_);
+        if (r_) return r_;
         break;
-      case 1:
-        KL(c->ops->dirac(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, nullptr, nullptr, c->sms, l, nullptr));
+      }
+      case 1: {
+        int np_ = 0;
+        int r_ = apply_op(c, fptr(c, h[0]), fptr(c, h[1]), 0.0, false, nullptr, l, nullptr, &np_);
+        if (r_) return r_;
         break;
+      }
       case 9:  // first-generation stencil (+ fused Gram), kept for comparison
         KL(c->ops->dirac_v1(c->stream, fptr(c, h[0]), fptr(c, h[1]), uptr(c), c->V, m2, 0.0, c->gpart, nullptr, c->sms, l));
         break;

@@ -843,14 +843,18 @@ shift_pipe_kernel(const __grid_constant__ ShiftMaps maps, const cd* __restrict__
   }
 }
 
-// Halo refresh for one rank: slots -2,-1,V,V+1 <- periodic images (any V >= 1).
-// `site` = complex numbers per site (3N for fields, 9 for links).
-static __global__ void halo_wrap_kernel(cd* __restrict__ f, long long V, int site, const Ctrl* __restrict__ ctrl) {
+// Halo refresh for one rank: slots -H..-1 and V..V+H-1 <- periodic images (any V >= 1).
+// `site` = complex numbers per site (3N for fields, 9 or 36 for links); H = 2 for the 1-D
+// chain, one x3-slice for the 4-D operator.
+static __global__ void halo_wrap_kernel(cd* __restrict__ f, long long V, int site, long long H,
+                                        const Ctrl* __restrict__ ctrl) {
   if (ctrl != nullptr && ctrl->done) return;
-  const int n = 4 * site;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int slot = i / site, e = i - slot * site;
-    const long long h = (slot < 2) ? (slot - 2) : (V + slot - 2);
+  const long long n = 2 * H * site;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long slot = i / site;
+    const int e = static_cast<int>(i - slot * site);
+    const long long h = (slot < H) ? (slot - H) : (V + slot - H);
     long long src = h % V;
     if (src < 0) src += V;
     f[h * site + e] = f[src * site + e];

@@ -5,6 +5,7 @@
 #include "field_kernels.cuh"
 #include "dirac_chain.cuh"
 #include "axpy_pipe.cuh"
+#include "dirac4d.cuh"
 
 namespace bcg {
 
@@ -21,6 +22,9 @@ struct OpsTable {
   // first-generation tile kernel (intermediate staged in shared memory), kept for comparison
   int (*dirac_v1)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
                   cd* gpart, const Ctrl* ctrl, int sms, int* launches);
+  // one sweep of the 4-D operator (dirac4d.cuh): second == 0: out = D in ; else out = (m2 + sigma) p0 - D in
+  int (*dirac4_sweep)(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* U, const Lattice4* lat,
+                      long long V, double m2, double sigma, int second, const Ctrl* ctrl, int* launches);
   int (*gram)(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
               int* launches);
   int (*axpy_gram)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
@@ -210,6 +214,18 @@ struct Ops {
     return grid < 1 ? 1 : grid;
   }
 
+  static int dirac4_sweep(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* U, const Lattice4* lat,
+                          long long V, double m2, double sigma, int second, const Ctrl* ctrl, int* launches) {
+    const long long items = V * (N / R);
+    const unsigned grid = static_cast<unsigned>((items + 127) / 128);
+    if (second)
+      dirac4_kernel<N, R, true><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, V, m2, sigma, ctrl);
+    else
+      dirac4_kernel<N, R, false><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, V, m2, sigma, ctrl);
+    if (launches) ++*launches;
+    return err();
+  }
+
   static int gram(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
                   int* launches) {
     prepare(sms);
@@ -376,6 +392,7 @@ const OpsTable* make_ops() {
                              Ops<N>::FUSED ? 1 : 0,
                              &Ops<N>::dirac,
                              &Ops<N>::dirac_v1,
+                             &Ops<N>::dirac4_sweep,
                              &Ops<N>::gram,
                              &Ops<N>::axpy_gram,
                              (Ops<N>::CHAIN && Ops<N>::APIPE) ? 1 : 0,

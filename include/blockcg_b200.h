@@ -67,6 +67,12 @@ int bcg_supports_nrhs(int n_rhs);
  * rank/nranks : position in the slab decomposition (0/1 for a single GPU). */
 int bcg_ctx_create(bcg_ctx** ctx, int64_t v_local, int n_rhs, int max_shifts, int device, int rank,
                    int nranks);
+/* 4-D extension (NOT in the reference, whose operator is a 1-D chain, inc/dirac_op.hpp:13-21):
+ * local lattice L0 x L1 x L2 x L3, x = x0 + L0 (x1 + L1 (x2 + L2 x3)), slab-decomposed along
+ * x3 (dims_local[3] = this rank's thickness), four links per site.  Every other entry point
+ * works unchanged on such a context; v_local = L0*L1*L2*L3. */
+int bcg_ctx_create_4d(bcg_ctx** ctx, const int64_t* dims_local /* [4] */, int n_rhs, int max_shifts, int device,
+                      int rank, int nranks);
 int bcg_ctx_destroy(bcg_ctx* ctx);
 const char* bcg_last_error(const bcg_ctx* ctx);
 
@@ -86,6 +92,9 @@ int bcg_comm_ipc_open(bcg_ctx* ctx, const void* handles /* nranks * BCG_IPC_HAND
 /* links_host: this rank's [v_local][3][3] links; halos (2 sites each side) are
  * filled by periodic wrap (1 rank) or neighbour exchange (nranks > 1). */
 int bcg_set_links(bcg_ctx* ctx, const double* links_host, double mass);
+/* 4-D context: links_host = [v_local][4][3][3] (direction-major per site, column-major 3x3);
+ * D v[x] = 1/2 sum_mu ( U_mu[x] v[x+mu] - U_mu[x-mu]^dag v[x-mu] ), operator m^2 - D^2. */
+int bcg_set_links_4d(bcg_ctx* ctx, const double* links_host, double mass);
 
 /* ---- device-resident fields --------------------------------------------------------- */
 int bcg_field_alloc(bcg_ctx* ctx, int* handle_out);

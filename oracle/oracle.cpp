@@ -39,8 +39,41 @@ double now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ---- 4-D extension (NOT in the reference => parity unpinned for this operator) ----
+// The reference's hop (inc/dirac_op.hpp:14-21) generalised from one direction to four on an
+// L0 x L1 x L2 x L3 periodic lattice, x = x0 + L0 (x1 + L1 (x2 + L2 x3)), four links per site
+// (U[x][mu], 3x3 column-major):
+//   D v[x] = 1/2 sum_mu ( U_mu[x] v[x + mu] - U_mu[x - mu]^dag v[x - mu] )
+// still exactly anti-Hermitian for any links, so m^2 - D^2 stays Hermitian positive definite.
+// g_dims[0] == 0 selects the reference's 1-D chain.
+int g_dims[4] = {0, 0, 0, 0};
+inline size_t u4idx(size_t x, int mu, int i, int j) { return (x * 4 + mu) * 9 + i + 3 * j; }
+void D4(int V, int N, const cd* U, const cd* in, cd* out) {
+  const int L[4] = {g_dims[0], g_dims[1], g_dims[2], g_dims[3]};
+  const long long stride[4] = {1, L[0], 1LL * L[0] * L[1], 1LL * L[0] * L[1] * L[2]};
+  for (int x = 0; x < V; ++x) {
+    int c[4] = {x % L[0], (x / L[0]) % L[1], static_cast<int>((x / stride[2]) % L[2]), static_cast<int>(x / stride[3])};
+    for (int r = 0; r < N; ++r)
+      for (int i = 0; i < 3; ++i) out[fidx(N, x, r, i)] = 0;
+    for (int mu = 0; mu < 4; ++mu) {
+      const int xp = static_cast<int>(x + ((c[mu] + 1 == L[mu]) ? -(L[mu] - 1) * stride[mu] : stride[mu]));
+      const int xm = static_cast<int>(x + ((c[mu] == 0) ? (L[mu] - 1) * stride[mu] : -stride[mu]));
+      for (int r = 0; r < N; ++r)
+        for (int i = 0; i < 3; ++i) {
+          cd a = 0, b = 0;
+          for (int j = 0; j < 3; ++j) {
+            a += (0.5 * U[u4idx(x, mu, i, j)]) * in[fidx(N, xp, r, j)];
+            b += (0.5 * std::conj(U[u4idx(xm, mu, j, i)])) * in[fidx(N, xm, r, j)];
+          }
+          out[fidx(N, x, r, i)] += a - b;
+        }
+    }
+  }
+}
+
 // inc/dirac_op.hpp:14-21  lhs[x] = 0.5 U[x] rhs[x+1] - 0.5 U[x-1]^dag rhs[x-1], periodic
 void D(int V, int N, const cd* U, const cd* in, cd* out) {
+  if (g_dims[0] > 0) return D4(V, N, U, in, out);
   for (int x = 0; x < V; ++x) {
     int xp = (x + 1) % V, xm = (x - 1 + V) % V;
     for (int r = 0; r < N; ++r)
@@ -310,6 +343,11 @@ void ora_op(int V, int N, double mass, const double* U, const double* in, double
   op(V, N, mass, C(U), C(in), C(out), sigma);
 }
 void ora_D(int V, int N, const double* U, const double* in, double* out) { D(V, N, C(U), C(in), C(out)); }
+// select the operator every function of this library applies: dims = NULL or dims[0] == 0: the
+// reference's 1-D chain (links [V][3][3]); else the 4-D extension (links [V][4][3][3])
+void ora_set_lattice(const int* dims) {
+  for (int m = 0; m < 4; ++m) g_dims[m] = dims ? dims[m] : 0;
+}
 void ora_hermitian_dot(int V, int N, const double* a, const double* b, double* R, int chunk) {
   hermitian_dot(V, N, C(a), C(b), C(R), chunk);
 }

@@ -57,6 +57,14 @@ class Oracle:
         L.ora_SBCGrQ.restype = C.c_int
         L.ora_llt_upper.restype = C.c_int
 
+    def set_lattice(self, dims=None):
+        """dims = (L0, L1, L2, L3): every later call applies the 4-D extension of the operator
+        (links (V, 4, 3, 3)); None: back to the reference's 1-D chain."""
+        if dims is None:
+            self.lib.ora_set_lattice(None)
+        else:
+            self.lib.ora_set_lattice((C.c_int * 4)(*[int(d) for d in dims]))
+
     def make_inputs(self, V, N, seed=1):
         U = np.empty((V, 3, 3), np.complex128)
         B = np.empty((V, N, 3), np.complex128)

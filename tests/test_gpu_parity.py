@@ -194,6 +194,40 @@ def test_reductions_are_bit_reproducible(bcg, oracle):
             assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("dims,N", [((4, 3, 2, 5), 2), ((6, 6, 6, 6), 12), ((8, 4, 6, 2), 8), ((5, 1, 3, 4), 3)])
+def test_4d_extension(bcg, oracle, dims, N):
+    """4-D extension of the operator (NOT in the reference: parity is against the CPU restatement
+    oracle/oracle.cpp:D4 only, plus the properties that define the construction -- D anti-Hermitian,
+    m^2 - D^2 Hermitian positive definite -- and the reference's acceptance rule true residual < 2*eps)."""
+    rng = np.random.default_rng(sum(dims) + N)
+    V = int(np.prod(dims))
+    U = rng.uniform(-1, 1, (V, 4, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 4, 3, 3))
+    B = rng.uniform(-1, 1, (V, N, 3)) + 1j * rng.uniform(-1, 1, (V, N, 3))
+    mass, eps = 0.3, 1e-10
+    shifts = [0.0, 0.05, 0.5]
+    oracle.set_lattice(dims)
+    try:
+        with bcg.Context(V, N, max_shifts=len(shifts), dims=dims) as ctx:
+            ctx.set_links(U, mass)
+            hb, ha = ctx.field(B), ctx.field()
+            G = ctx.op(ha, hb, sigma=0.25, want_gram=True)
+            AB = oracle.op(U, B, mass, 0.25)
+            assert rel(ctx.download(ha), AB) < 1e-13
+            assert rel(G, oracle.hermitian_dot(B, AB)) < 1e-12
+            assert np.abs(G - G.conj().T).max() / np.abs(G).max() < 1e-13 and np.all(G.diagonal().real > 0)
+            xs = [ctx.field() for _ in shifts]
+            info = ctx.solve_sbcgrq_dev(xs, hb, shifts, eps, 1e-15)
+            Xo, ito, _, _ = oracle.SBCGrQ(U, B, mass, shifts, eps, 1e-15, chunk=32)
+            assert abs(info.iterations - ito) <= 1
+            for s, sig in enumerate(shifts):
+                X = ctx.download(xs[s])
+                assert rel(X, Xo[s]) < 1e-9
+                assert oracle.true_residual(U, B, X, mass, sig).max() < 2 * eps
+                assert ctx.true_residual(xs[s], hb, sig).max() < 2 * eps
+    finally:
+        oracle.set_lattice(None)
+
+
 def test_full_size_properties(bcg, oracle):
     """BASELINE config sizes (16^4, N=12): properties that need no CPU solve."""
     V, N, mass = 16 ** 4, 12, 1e-3

@@ -98,3 +98,39 @@ def test_oracle_vs_live_reference(oracle, N):
     Xr, itr, _ = r.BCG(U, B, mass, 1e-10)
     Xo, ito, _ = oracle.BCG(U, B, mass, 1e-10)
     assert abs(itr - ito) <= 1 and rel(Xo, Xr) < 1e-9
+
+
+def test_4d_extension_properties(oracle):
+    """The 4-D extension of the operator has no reference counterpart (its oracle is 'parity
+    unpinned'); what pins it are the properties of the construction: D anti-Hermitian for any
+    links, m^2 - D^2 Hermitian positive definite with spectrum >= m^2, a 1 x 1 x 1 lattice in
+    three directions degenerating to independent chains, and convergence of the solvers."""
+    rng = np.random.default_rng(11)
+    dims, N, mass = (4, 3, 2, 5), 2, 0.3
+    V = int(np.prod(dims))
+    U = rng.uniform(-1, 1, (V, 4, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 4, 3, 3))
+    a = rng.standard_normal((V, N, 3)) + 1j * rng.standard_normal((V, N, 3))
+    b = rng.standard_normal((V, N, 3)) + 1j * rng.standard_normal((V, N, 3))
+    oracle.set_lattice(dims)
+    try:
+        Da, Db = oracle.D(U, a), oracle.D(U, b)
+        assert abs(np.vdot(a, Db) + np.vdot(Da, b)) < 1e-12 * abs(np.vdot(a, Db))
+        Aa, Ab = oracle.op(U, a, mass), oracle.op(U, b, mass)
+        assert abs(np.vdot(b, Aa) - np.vdot(Ab, a)) < 1e-12 * abs(np.vdot(b, Aa))
+        assert np.vdot(a, Aa).real >= mass * mass * np.vdot(a, a).real
+        shifts = [0.0, 0.1]
+        Xs, it, _, _ = oracle.SBCGrQ(U, a, mass, shifts, 1e-10, 1e-15)
+        for s, sig in enumerate(shifts):
+            assert oracle.true_residual(U, a, Xs[s], mass, sig).max() < 2e-10
+        # along one direction only, with the other three links zero, D is the reference's chain
+        V1 = 7
+        oracle.set_lattice((V1, 1, 1, 1))
+        U1 = rng.uniform(-1, 1, (V1, 3, 3)) + 1j * rng.uniform(-1, 1, (V1, 3, 3))
+        U4 = np.zeros((V1, 4, 3, 3), np.complex128)
+        U4[:, 0] = U1
+        x = rng.standard_normal((V1, N, 3)) + 1j * rng.standard_normal((V1, N, 3))
+        D4x = oracle.D(U4, x)
+        oracle.set_lattice(None)
+        assert np.abs(D4x - oracle.D(U1, x)).max() < 1e-14
+    finally:
+        oracle.set_lattice(None)
