@@ -41,7 +41,34 @@ def main():
     res["x_rel"] = [float(np.abs(ctx.download(xs[s]) - Xo[s][b:e]).max() / np.abs(Xo[s]).max()) for s in range(len(shifts))]
     res["true_res"] = [float(ctx.true_residual(xs[s], hb, shifts[s]).max()) for s in range(len(shifts))]
     res["solve_ms"] = info.solve_ms
-    ok = (res["op_rel"] < 1e-13 and res["gram_rel"] < 1e-12 and max(res["x_rel"]) < 1e-9
+    # ---- 4-D extension: t-slabs (x3 slowest), halo = one x3-slice per side, two sweeps per apply ----
+    dims = (6, 4, 6, 2 * world)
+    V4 = int(np.prod(dims))
+    rng = np.random.default_rng(3)
+    U4 = rng.uniform(-1, 1, (V4, 4, 3, 3)) + 1j * rng.uniform(-1, 1, (V4, 4, 3, 3))
+    B4 = rng.uniform(-1, 1, (V4, N, 3)) + 1j * rng.uniform(-1, 1, (V4, N, 3))
+    sl = dims[0] * dims[1] * dims[2]
+    b4, e4 = rank * 2 * sl, (rank + 1) * 2 * sl
+    ctx4 = blockcg_b200.Context(0, N, max_shifts=2, device=local, rank=rank, nranks=world, dims=dims[:3] + (2,))
+    ctx4.comm_init(D.broadcast_unique_id(dist, torch.device("cuda", local)))
+    ctx4.set_links(np.ascontiguousarray(U4[b4:e4]), 0.3)
+    o.set_lattice(dims)
+    h4b, h4a = ctx4.field(np.ascontiguousarray(B4[b4:e4])), ctx4.field()
+    G4 = ctx4.op(h4a, h4b, sigma=0.25, want_gram=True)
+    AB4 = o.op(U4, B4, 0.3, 0.25)
+    res["op4_rel"] = float(np.abs(ctx4.download(h4a) - AB4[b4:e4]).max() / np.abs(AB4).max())
+    G4ref = o.hermitian_dot(B4, AB4)
+    res["gram4_rel"] = float(np.abs(G4 - G4ref).max() / np.abs(G4ref).max())
+    x4 = [ctx4.field(), ctx4.field()]
+    info4 = ctx4.solve_sbcgrq_dev(x4, h4b, [0.0, 0.1], 1e-10, 1e-15)
+    Xo4, ito4, _, _ = o.SBCGrQ(U4, B4, 0.3, [0.0, 0.1], 1e-10, 1e-15, chunk=32)
+    o.set_lattice(None)
+    res["iterations4"], res["oracle_iterations4"] = info4.iterations, ito4
+    res["x4_rel"] = [float(np.abs(ctx4.download(x4[s]) - Xo4[s][b4:e4]).max() / np.abs(Xo4[s]).max()) for s in range(2)]
+    ok4 = (res["op4_rel"] < 1e-13 and res["gram4_rel"] < 1e-12 and max(res["x4_rel"]) < 1e-9
+           and abs(info4.iterations - ito4) <= 2)
+    ctx4.close()
+    ok = ok4 and (res["op_rel"] < 1e-13 and res["gram_rel"] < 1e-12 and max(res["x_rel"]) < 1e-9
           and abs(info.iterations - ito) <= max(2, ito // 100) and max(res["true_res"]) < 2e-10)
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
