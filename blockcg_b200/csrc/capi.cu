@@ -115,6 +115,8 @@ struct bcg_ctx {
   double mass = 0.0;
   bool links_set = false;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // 4-D slabs: halo exchange overlapped with the interior sweeps
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   const OpsTable* ops = nullptr;
   cd* U_alloc = nullptr;
   std::vector<cd*> fields;  // allocation base (halo included); site 0 at +2*3N
@@ -346,10 +348,32 @@ int apply_op(bcg_ctx* c, cd* in, cd* out, double sigma, bool want_gram, const Ct
     if (r) return r;
   }
   cd* tmp = fptr(c, c->work_D);
-  KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, c->V, m2, sigma, 0, ctrl, launches));
-  int r = halo_refresh(c, tmp, 3 * c->N, ctrl, launches);
-  if (r) return r;
-  KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, c->V, m2, sigma, 1, ctrl, launches));
+  const long long H = c->halo, V = c->V;
+  if (c->nranks > 1 && c->lat.L3 >= 3) {
+    // Slab decomposition: the halo exchange of the intermediate field is overlapped with the
+    // interior.  Boundary slices of sweep 1 first; their exchange (NVLink, second stream) runs
+    // while both sweeps of the interior slices are computed; boundary slices of sweep 2 last.
+    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, 0, H, m2, sigma, 0, ctrl, launches));
+    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, V - H, V, m2, sigma, 0, ctrl, launches));
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream2;  // halo_refresh issues on c->stream
+    int r = halo_refresh(c, tmp, 3 * c->N, ctrl, launches);
+    c->stream = main_stream;
+    if (r) return r;
+    CU(cudaEventRecord(c->ev_join, c->stream2));
+    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, H, V - H, m2, sigma, 0, ctrl, launches));
+    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, H, V - H, m2, sigma, 1, ctrl, launches));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, 0, H, m2, sigma, 1, ctrl, launches));
+    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, V - H, V, m2, sigma, 1, ctrl, launches));
+  } else {
+    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, 0, V, m2, sigma, 0, ctrl, launches));
+    int r = halo_refresh(c, tmp, 3 * c->N, ctrl, launches);
+    if (r) return r;
+    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, 0, V, m2, sigma, 1, ctrl, launches));
+  }
   *np_out = 0;
   if (want_gram) {
     int np = c->ops->gram(c->stream, in, out, c->V, c->gpart, ctrl, c->sms, launches);
@@ -447,6 +471,9 @@ static int ctx_create(bcg_ctx** out, int64_t v_local, const int64_t* dims, int n
   c->cap = c->ops->field_capacity(c->V, c->sms);
   if (c->cap < c->V + c->halo) c->cap = c->V + c->halo;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   c->L.N = n_rhs;
   c->L.S = max_shifts;
   c->gpart_elems = static_cast<size_t>(c->ops->max_partials(c->sms)) * c->L.nn();
@@ -512,6 +539,9 @@ int bcg_ctx_destroy(bcg_ctx* c) {
     if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_batch)
     if (e) cudaEventDestroy(e);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return BCG_OK;

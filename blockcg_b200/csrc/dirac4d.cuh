@@ -28,14 +28,16 @@ struct Lattice4 {
 template <int N, int R, bool SECOND>
 __global__ void __launch_bounds__(128)
 dirac4_kernel(const cd* __restrict__ in, const cd* __restrict__ p0, cd* __restrict__ out,
-              const cd* __restrict__ U, Lattice4 lat, long long V, double m2, double sigma,
+              const cd* __restrict__ U, Lattice4 lat, long long x_begin, long long x_end, double m2, double sigma,
               const Ctrl* __restrict__ ctrl) {
+  // sites [x_begin, x_end): the whole local volume, or a range of x3-slices when the halo
+  // exchange of the boundary slices is overlapped with the interior
   constexpr int G = N / R, SITE = 3 * N;
   if (ctrl != nullptr && (ctrl->done | ctrl->stop)) return;
   const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (item >= V * G) return;
-  const long long x = item / G;
-  const int g = static_cast<int>(item - x * G);
+  if (item >= (x_end - x_begin) * G) return;
+  const long long x = x_begin + item / G;
+  const int g = static_cast<int>(item % G);
   const int col0 = g * R * 3;
   const int x0 = static_cast<int>(x % lat.L0);
   const long long q1 = x / lat.L0;

@@ -23,8 +23,10 @@ struct OpsTable {
   int (*dirac_v1)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
                   cd* gpart, const Ctrl* ctrl, int sms, int* launches);
   // one sweep of the 4-D operator (dirac4d.cuh): second == 0: out = D in ; else out = (m2 + sigma) p0 - D in
+  // (sites [x_begin, x_end) only)
   int (*dirac4_sweep)(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* U, const Lattice4* lat,
-                      long long V, double m2, double sigma, int second, const Ctrl* ctrl, int* launches);
+                      long long x_begin, long long x_end, double m2, double sigma, int second, const Ctrl* ctrl,
+                      int* launches);
   int (*gram)(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
               int* launches);
   int (*axpy_gram)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
@@ -215,13 +217,15 @@ struct Ops {
   }
 
   static int dirac4_sweep(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* U, const Lattice4* lat,
-                          long long V, double m2, double sigma, int second, const Ctrl* ctrl, int* launches) {
-    const long long items = V * (N / R);
+                          long long x_begin, long long x_end, double m2, double sigma, int second, const Ctrl* ctrl,
+                          int* launches) {
+    if (x_end <= x_begin) return 0;
+    const long long items = (x_end - x_begin) * (N / R);
     const unsigned grid = static_cast<unsigned>((items + 127) / 128);
     if (second)
-      dirac4_kernel<N, R, true><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, V, m2, sigma, ctrl);
+      dirac4_kernel<N, R, true><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
     else
-      dirac4_kernel<N, R, false><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, V, m2, sigma, ctrl);
+      dirac4_kernel<N, R, false><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
     if (launches) ++*launches;
     return err();
   }

@@ -42,14 +42,14 @@ def main():
     res["true_res"] = [float(ctx.true_residual(xs[s], hb, shifts[s]).max()) for s in range(len(shifts))]
     res["solve_ms"] = info.solve_ms
     # ---- 4-D extension: t-slabs (x3 slowest), halo = one x3-slice per side, two sweeps per apply ----
-    dims = (6, 4, 6, 2 * world)
+    dims = (6, 4, 6, 4 * world)
     V4 = int(np.prod(dims))
     rng = np.random.default_rng(3)
     U4 = rng.uniform(-1, 1, (V4, 4, 3, 3)) + 1j * rng.uniform(-1, 1, (V4, 4, 3, 3))
     B4 = rng.uniform(-1, 1, (V4, N, 3)) + 1j * rng.uniform(-1, 1, (V4, N, 3))
     sl = dims[0] * dims[1] * dims[2]
-    b4, e4 = rank * 2 * sl, (rank + 1) * 2 * sl
-    ctx4 = blockcg_b200.Context(0, N, max_shifts=2, device=local, rank=rank, nranks=world, dims=dims[:3] + (2,))
+    b4, e4 = rank * 4 * sl, (rank + 1) * 4 * sl
+    ctx4 = blockcg_b200.Context(0, N, max_shifts=2, device=local, rank=rank, nranks=world, dims=dims[:3] + (4,))
     ctx4.comm_init(D.broadcast_unique_id(dist, torch.device("cuda", local)))
     ctx4.set_links(np.ascontiguousarray(U4[b4:e4]), 0.3)
     o.set_lattice(dims)
