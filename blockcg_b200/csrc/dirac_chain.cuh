@@ -230,7 +230,7 @@ struct ChainGeom {
   static constexpr int NBAR_IN = 4, NBAR_G = 4;
   static constexpr int P_ELEMS = SP * K * PP, U_ELEMS = SU * K * PU, O_ELEMS = SO * K * PP;
   static constexpr size_t SMEM_BYTES =
-      sizeof(cd) * (P_ELEMS + U_ELEMS + O_ELEMS) + 8 * (NBAR_IN + 2 + NBAR_G + 2) + 16;
+      sizeof(cd) * (P_ELEMS + U_ELEMS + O_ELEMS) + 8 * (NBAR_IN + SO + NBAR_G + SO) + 16;
   static constexpr int ROWS = 3 * K * W;          // Gram rows per tile
   // lanes of a quarter warp must hit 8 distinct 16-byte bank groups when they read their P
   // columns: when consecutive sites are 4 (mod 8) units apart the parity bit goes inside
@@ -255,15 +255,15 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   cd* sO = sU + Geo::U_ELEMS;
   uint64_t* inb = reinterpret_cast<uint64_t*>(sO + Geo::O_ELEMS);
   uint64_t* ofull = inb + Geo::NBAR_IN;
-  uint64_t* gdone = ofull + 2;
+  uint64_t* gdone = ofull + SO;
   uint64_t* sdone = gdone + Geo::NBAR_G;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < Geo::NBAR_IN; ++i) mbar_init(inb + i, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(ofull + i, Geo::NSW);
+    for (int i = 0; i < SO; ++i) mbar_init(ofull + i, Geo::NSW);
     for (int i = 0; i < Geo::NBAR_G; ++i) mbar_init(gdone + i, GRAM ? Geo::NGW : Geo::NSW);
-    for (int i = 0; i < 2; ++i) mbar_init(sdone + i, 1);
+    for (int i = 0; i < SO; ++i) mbar_init(sdone + i, 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -304,11 +304,11 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     // the pad element of every window row lies outside dimension 0 of the view: not written
     if (lane != 0) return;
     for (int t = 0; t < T; ++t) {
-      mbar_wait(ofull + (t & 1), static_cast<uint32_t>((t >> 1) & 1));
+      mbar_wait(ofull + (t % SO), static_cast<uint32_t>((t / SO) & 1));
       tma_store_3d(&tmO, 0, t, q0, sO + (t % SO) * (K * PP));
       bulk_commit();
       bulk_wait_read0();  // shared memory of this tile has been read
-      mbar_arrive(sdone + (t & 1));
+      mbar_arrive(sdone + (t % SO));
     }
     bulk_wait0();
     return;
@@ -322,7 +322,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     auto gram_loop = [&](auto& part) {
       part.init();
       for (int t = 0; t < T; ++t) {
-        mbar_wait(ofull + (t & 1), static_cast<uint32_t>((t >> 1) & 1));
+        mbar_wait(ofull + (t % SO), static_cast<uint32_t>((t / SO) & 1));
         const cd* tP = sP + (t % SP) * (K * PP);  // P-load t holds P at this tile's out sites
         const cd* tO = sO + (t % SO) * (K * PP);
         // not unrolled: four different Gram loops plus the stencil loop must stay resident in the
@@ -405,9 +405,9 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
   for (int t = 0; t < T; ++t) {
     mbar_wait(inb + (t & 3), static_cast<uint32_t>((t >> 2) & 1));
-    if (t >= 2) {  // T window slot free again: Gram and store of tile t-2 are through with it
-      if (GRAM) mbar_wait(gdone + ((t - 2) & 3), static_cast<uint32_t>(((t - 2) >> 2) & 1));
-      mbar_wait(sdone + (t & 1), static_cast<uint32_t>(((t - 2) >> 1) & 1));
+    if (t >= SO) {  // T window slot free again: Gram and store of tile t-SO are through with it
+      if (GRAM) mbar_wait(gdone + ((t - SO) & 3), static_cast<uint32_t>(((t - SO) >> 2) & 1));
+      mbar_wait(sdone + (t % SO), static_cast<uint32_t>(((t - SO) / SO) & 1));
     }
     const cd* tP0 = sP + (t % SP) * (K * PP) + k * PP;         // P at out sites o0 .. o0+W
     const cd* tP1 = sP + ((t + 1) % SP) * (K * PP) + k * PP;   // P at o0+W .. o0+2W
@@ -458,7 +458,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     fence_proxy_async();  // T window visible to the bulk store
     __syncwarp();
     if (lane == 0) {
-      mbar_arrive(ofull + (t & 1));
+      mbar_arrive(ofull + (t % SO));
       if (!GRAM) mbar_arrive(gdone + (t & 3));  // no Gram warps: the stencil releases the input slots itself
     }
   }
