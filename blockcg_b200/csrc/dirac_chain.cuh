@@ -238,13 +238,22 @@ struct ChainGeom {
   static constexpr bool PARITY_INNER = (G != 4) || (SITE % 8 == 4);
 };
 
-template <int N, int G, int K, int W, bool GRAM>
-__global__ void __launch_bounds__(ChainGeom<N, G, K, W>::NT, 1)
+// GMODE 0: no Gram.  1: four dedicated Gram warps working one tile behind the stencil warps.
+// 2 (experiment, not built by default): no dedicated warps -- after each tile the four stencil
+// warps wait for one another and compute one GramPart each over the tile they have just
+// finished, accumulators in their own registers (255 per thread with 6 warps per CTA).  Measured
+// 3x SLOWER than mode 1 (334 vs 106 us at 24^4, N=12): every warp then runs its own ~18 KB copy
+// of stencil + Gram loop, which no longer fits the per-sub-partition instruction cache.  The
+// lesson cuts the other way too: hot loops are kept small and rolled wherever that is free.
+template <int N, int G, int K, int W, int GMODE>
+__global__ void __launch_bounds__((GMODE == 2 ? (ChainGeom<N, G, K, W>::NSW + 2) * 32 : ChainGeom<N, G, K, W>::NT), 1)
 dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmU, const cd* __restrict__ in,
                    const cd* __restrict__ U, long long V, long long L, double m2, double sigma,
                    cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl, const GramPeers peers) {
   using Geo = ChainGeom<N, G, K, W>;
+  constexpr int WARP_LOAD = (GMODE == 2) ? Geo::NSW : Geo::WARP_LOAD;
+  constexpr int WARP_STORE = WARP_LOAD + 1;
   constexpr int R = Geo::R, SITE = Geo::SITE, PP = Geo::PP, PU = Geo::PU;
   constexpr int SP = Geo::SP, SU = Geo::SU, SO = Geo::SO;
   if (ctrl != nullptr && (ctrl->done | ctrl->stop)) return;
@@ -262,7 +271,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (tid == 0) {
     for (int i = 0; i < Geo::NBAR_IN; ++i) mbar_init(inb + i, 1);
     for (int i = 0; i < SO; ++i) mbar_init(ofull + i, Geo::NSW);
-    for (int i = 0; i < Geo::NBAR_G; ++i) mbar_init(gdone + i, GRAM ? Geo::NGW : Geo::NSW);
+    for (int i = 0; i < Geo::NBAR_G; ++i) mbar_init(gdone + i, GMODE == 1 ? Geo::NGW : Geo::NSW);
     for (int i = 0; i < SO; ++i) mbar_init(sdone + i, 1);
     mbar_fence_init();
   }
@@ -280,7 +289,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   constexpr uint32_t P_BOX_BYTES = K * PP * sizeof(cd), U_BOX_BYTES = K * PU * sizeof(cd);
   const int q0 = static_cast<int>(chain0);
 
-  if (warp == Geo::WARP_LOAD) {
+  if (warp == WARP_LOAD) {
     // ===================== loader: three tensor copies per tile, one elected lane =====================
     // input barrier of tile t covers P-load t+1 (sites o0+W .. o0+2W) and link-load t
     // (links o0-1 .. o0+W+1) of all K sub-chains; tile 0 also brings P-load 0.
@@ -299,7 +308,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     return;
   }
 
-  if (warp == Geo::WARP_STORE) {
+  if (warp == WARP_STORE) {
     // ===================== storer: one tensor store per tile =====================
     // the pad element of every window row lies outside dimension 0 of the view: not written
     if (lane != 0) return;
@@ -316,7 +325,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
   if (warp >= Geo::NSW) {
     // ===================== Gram warps: block (ti,tj) of P^dag T =====================
-    if (!GRAM) return;
+    if (GMODE != 1) return;
     // row = (colour c, site s of the window, sub-chain k), k fastest across lanes: the 8 lanes of a
     // quarter warp read 8 consecutive windows, which start on 8 different 16-byte bank groups
     auto gram_loop = [&](auto& part) {
@@ -355,112 +364,154 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   }
 
   // ===================== stencil warps =====================
-  int g, p, kq;
-  {
-    const int l8 = lane & 7, q8 = lane >> 3;
-    if (G == 4) {
-      g = l8 & 3;
-      if (Geo::PARITY_INNER) {
-        p = l8 >> 2;
-        kq = q8;
+  struct NoPart {
+    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void row(const cd*, const cd*) {}
+    __device__ __forceinline__ void store(cd*, cd*) {}
+  };
+  auto stencil = [&](auto& part) {
+    part.init();
+    int g, p, kq;
+    {
+      const int l8 = lane & 7, q8 = lane >> 3;
+      if (G == 4) {
+        g = l8 & 3;
+        if (Geo::PARITY_INNER) {
+          p = l8 >> 2;
+          kq = q8;
+        } else {
+          p = q8 & 1;
+          kq = (q8 >> 1) * 2 + (l8 >> 2);
+        }
       } else {
-        p = q8 & 1;
-        kq = (q8 >> 1) * 2 + (l8 >> 2);
+        g = lane % G;
+        p = (lane / G) & 1;
+        kq = lane / (2 * G);
       }
-    } else {
-      g = lane % G;
-      p = (lane / G) & 1;
-      kq = lane / (2 * G);
     }
-  }
-  const int k = warp * Geo::KW + kq;
-  const long long cs = chain_start(k);
-  const long long rem_ll = chain_end(k) - cs;
-  const int rem = rem_ll < 0 ? 0 : static_cast<int>(rem_ll);  // valid out sites of this sub-chain
-  const int col0 = g * R * 3;  // first complex of this thread's columns inside a site
-  const double ms = m2;
+    const int k = warp * Geo::KW + kq;
+    const long long cs = chain_start(k);
+    const long long rem_ll = chain_end(k) - cs;
+    const int rem = rem_ll < 0 ? 0 : static_cast<int>(rem_ll);  // valid out sites of this sub-chain
+    const int col0 = g * R * 3;  // first complex of this thread's columns inside a site
+    const double ms = m2;
 
-  cd tm[R][3];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) tm[r][c] = czero();
-  if (p < rem) {
-    // chain start: (D P)[x-1] for the first site of this chain, straight from global memory
-    const long long x = cs + p;
-    cd v[R][3], acc[R][3];
+    cd tm[R][3];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[r][c] = czero();
-    load_cols<N, R>(in + x * SITE + col0, v);
-    apply_link<R>(U + (x - 1) * 9, v, acc);
-    load_cols<N, R>(in + (x - 2) * SITE + col0, v);
-    apply_link_dag_sub<R>(U + (x - 2) * 9, v, acc);
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) tm[r][c] = cscale(acc[r][c], 0.5);
-  }
-
-  for (int t = 0; t < T; ++t) {
-    mbar_wait(inb + (t & 3), static_cast<uint32_t>((t >> 2) & 1));
-    if (t >= SO) {  // T window slot free again: Gram and store of tile t-SO are through with it
-      if (GRAM) mbar_wait(gdone + ((t - SO) & 3), static_cast<uint32_t>(((t - SO) >> 2) & 1));
-      mbar_wait(sdone + (t % SO), static_cast<uint32_t>(((t - SO) / SO) & 1));
-    }
-    const cd* tP0 = sP + (t % SP) * (K * PP) + k * PP;         // P at out sites o0 .. o0+W
-    const cd* tP1 = sP + ((t + 1) % SP) * (K * PP) + k * PP;   // P at o0+W .. o0+2W
-    const cd* tU = sU + (t % SU) * (K * PU) + k * PU;          // links o0-1 .. o0+W+1
-    cd* tO = sO + (t % SO) * (K * PP) + k * PP;
-#pragma unroll
-    for (int i = 0; i < W / 2; ++i) {
-      const int ls = p + 2 * i;  // out site o0 + ls
-      cd v[R][3], tp[R][3], acc[R][3];
-      // tp = 1/2 (U[x+1] P[x+2] - U[x]^dag P[x])
+      for (int c = 0; c < 3; ++c) tm[r][c] = czero();
+    if (p < rem) {
+      // chain start: (D P)[x-1] for the first site of this chain, straight from global memory
+      const long long x = cs + p;
+      cd v[R][3], acc[R][3];
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) acc[r][c] = czero();
-      load_cols<N, R>((ls + 2 < W ? tP0 + (ls + 2) * SITE : tP1 + (ls + 2 - W) * SITE) + col0, v);
-      apply_link<R>(tU + (ls + 2) * 9, v, acc);
-      load_cols<N, R>(tP0 + ls * SITE + col0, v);
-      apply_link_dag_sub<R>(tU + (ls + 1) * 9, v, acc);
+      load_cols<N, R>(in + x * SITE + col0, v);
+      apply_link<R>(U + (x - 1) * 9, v, acc);
+      load_cols<N, R>(in + (x - 2) * SITE + col0, v);
+      apply_link_dag_sub<R>(U + (x - 2) * 9, v, acc);
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tp[r][c] = cscale(acc[r][c], 0.5);
-      // T[x] = (m^2 + sigma) P[x] - 1/2 (U[x] tp - U[x-1]^dag tm)
+        for (int c = 0; c < 3; ++c) tm[r][c] = cscale(acc[r][c], 0.5);
+    }
+
+    for (int t = 0; t < T; ++t) {
+      mbar_wait(inb + (t & 3), static_cast<uint32_t>((t >> 2) & 1));
+      if (t >= SO) {  // T window slot free again: Gram and store of tile t-SO are through with it
+        if (GMODE == 1) mbar_wait(gdone + ((t - SO) & 3), static_cast<uint32_t>(((t - SO) >> 2) & 1));
+        mbar_wait(sdone + (t % SO), static_cast<uint32_t>(((t - SO) / SO) & 1));
+      }
+      const cd* tP0 = sP + (t % SP) * (K * PP) + k * PP;         // P at out sites o0 .. o0+W
+      const cd* tP1 = sP + ((t + 1) % SP) * (K * PP) + k * PP;   // P at o0+W .. o0+2W
+      const cd* tU = sU + (t % SU) * (K * PU) + k * PU;          // links o0-1 .. o0+W+1
+      cd* tO = sO + (t % SO) * (K * PP) + k * PP;
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) acc[r][c] = czero();
-      apply_link<R>(tU + (ls + 1) * 9, tp, acc);
-      apply_link_dag_sub<R>(tU + ls * 9, tm, acc);
-      {  // sites past the end of the field land in the allocation slack (never read back)
-        cd* o = tO + ls * SITE + col0;
+      for (int i = 0; i < W / 2; ++i) {
+        const int ls = p + 2 * i;  // out site o0 + ls
+        cd v[R][3], tp[R][3], acc[R][3];
+        // tp = 1/2 (U[x+1] P[x+2] - U[x]^dag P[x])
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            // lhs = -D(D rhs) + m^2 rhs (dirac_op.hpp:42), then += sigma rhs (block_solvers.hpp:136)
-            cd tt = cmake(fma(ms, v[r][c].x, -0.5 * acc[r][c].x), fma(ms, v[r][c].y, -0.5 * acc[r][c].y));
-            tt.x = fma(sigma, v[r][c].x, tt.x);
-            tt.y = fma(sigma, v[r][c].y, tt.y);
-            o[r * 3 + c] = tt;
-          }
+          for (int c = 0; c < 3; ++c) acc[r][c] = czero();
+        load_cols<N, R>((ls + 2 < W ? tP0 + (ls + 2) * SITE : tP1 + (ls + 2 - W) * SITE) + col0, v);
+        apply_link<R>(tU + (ls + 2) * 9, v, acc);
+        load_cols<N, R>(tP0 + ls * SITE + col0, v);
+        apply_link_dag_sub<R>(tU + (ls + 1) * 9, v, acc);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tp[r][c] = cscale(acc[r][c], 0.5);
+        // T[x] = (m^2 + sigma) P[x] - 1/2 (U[x] tp - U[x-1]^dag tm)
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[r][c] = czero();
+        apply_link<R>(tU + (ls + 1) * 9, tp, acc);
+        apply_link_dag_sub<R>(tU + ls * 9, tm, acc);
+        {  // sites past the end of the field land in the allocation slack (never read back)
+          cd* o = tO + ls * SITE + col0;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              // lhs = -D(D rhs) + m^2 rhs (dirac_op.hpp:42), then += sigma rhs (block_solvers.hpp:136)
+              cd tt = cmake(fma(ms, v[r][c].x, -0.5 * acc[r][c].x), fma(ms, v[r][c].y, -0.5 * acc[r][c].y));
+              tt.x = fma(sigma, v[r][c].x, tt.x);
+              tt.y = fma(sigma, v[r][c].y, tt.y);
+              o[r * 3 + c] = tt;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) tm[r][c] = tp[r][c];
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) tm[r][c] = tp[r][c];
+      fence_proxy_async();  // T window visible to the bulk store
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(ofull + (t % SO));
+        if (GMODE == 0) mbar_arrive(gdone + (t & 3));  // no Gram: the stencil releases the input slots itself
+      }
+      if (GMODE == 2) {
+        // every stencil warp has written its T windows of tile t: this warp's quarter of the Gram
+        mbar_wait(ofull + (t % SO), static_cast<uint32_t>((t / SO) & 1));
+        const cd* gP = sP + (t % SP) * (K * PP);
+        const cd* gO = sO + (t % SO) * (K * PP);
+#pragma unroll 1
+        for (int it = 0; it < (Geo::ROWS + 31) / 32; ++it) {
+          const int rr = lane + 32 * it;
+          const int gk = rr % K, gs = (rr / K) % W, gc = rr / (K * W);
+          const long long grem = chain_end(gk) - chain_start(gk);
+          if (rr < Geo::ROWS && t * W + gs < grem) {
+            const int base = gk * PP + gs * SITE + gc;
+            part.row(gP + base, gO + base);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gdone + (t & 3));
+      }
     }
-    fence_proxy_async();  // T window visible to the bulk store
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(ofull + (t % SO));
-      if (!GRAM) mbar_arrive(gdone + (t & 3));  // no Gram warps: the stencil releases the input slots itself
+    if (GMODE == 2) {
+      part.store(gpart + (static_cast<size_t>(kGramRawOff) + blockIdx.x) * N * N, sP + ((T + warp) % SP) * (K * PP));
+      gram_group_reduce<N>(gpart, warp, peers, ctrl, 0);
     }
+  };
+  if constexpr (GMODE == 2) {
+    static_assert(GMODE != 2 || Geo::NSW == 4, "one GramPart per stencil warp");
+    switch (warp) {
+      case 0: { GramPart<N, 0> part; stencil(part); break; }
+      case 1: { GramPart<N, 1> part; stencil(part); break; }
+      case 2: { GramPart<N, 2> part; stencil(part); break; }
+      default: { GramPart<N, 3> part; stencil(part); break; }
+    }
+  } else {
+    NoPart part;
+    stencil(part);
   }
 }
 

@@ -103,6 +103,10 @@ inline int make_pair_map(CUtensorMap* m, const cd* base, int site, int box, long
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(cudaErrorInvalidValue);
 }
 
+#ifndef BCG_CHAIN_GMODE
+#define BCG_CHAIN_GMODE 1
+#endif
+
 #ifdef BCG_N  // ---- per-N implementation, included only by inst.cu ----------------------------
 
 constexpr int kNT = 192;  // 6 warps: one 4x4 Gram block per warp at N = 12, whole sites per CTA
@@ -145,6 +149,8 @@ struct Ops {
   static constexpr bool CHAIN = Tune<N>::CHAIN_G > 0;
   static constexpr int CG_ = CHAIN ? Tune<N>::CHAIN_G : 1, CK = Tune<N>::CHAIN_K, CW = Tune<N>::CHAIN_W;
   using CGm = ChainGeom<N, CG_, CHAIN ? CK : 16 / CG_, CW>;
+  static constexpr int CGMODE = BCG_CHAIN_GMODE;  // how the fused Gram is scheduled (dirac_chain.cuh)
+  static constexpr int CNT_G = (CGMODE == 2) ? (CGm::NSW + 2) * 32 : CGm::NT;
 
   // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
   // outside any stream capture -- and used to size the persistent grids.
@@ -176,9 +182,9 @@ struct Ops {
                            (int)APG::SMEM_BYTES);
     }
     if constexpr (CHAIN) {
-      cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, CGMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)CGm::SMEM_BYTES);
-      cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)CGm::SMEM_BYTES);
     }
   }
@@ -253,10 +259,10 @@ struct Ops {
       if (!e) e = make_chain_map(&tmU, U - 9, (CW + 2) * 9, CW * 9, CGm::PU, pl.T, pl.nchains + 1, CK);
       if (e) return e;
       if (gpart != nullptr)
-        dirac_chain_kernel<N, CG_, CK, CW, true><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
+        dirac_chain_kernel<N, CG_, CK, CW, CGMODE><<<pl.grid, CNT_G, CGm::SMEM_BYTES, st>>>(
             tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
       else
-        dirac_chain_kernel<N, CG_, CK, CW, false><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
+        dirac_chain_kernel<N, CG_, CK, CW, 0><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
             tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl, pe);
       if (launches) ++*launches;
       e = err();
