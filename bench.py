@@ -159,10 +159,14 @@ def run_reference(args, w, wname):
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
+EXCHANGE = ("halo sites and Gram blocks exchanged by P2P stores over NVLink from inside the kernels "
+            "(NCCL only in the set-up)")
+
+
 def config_of(wname, w, gpus):
     return {"workload": wname, "V": w["V"], "n_rhs": w["N"], "n_shifts": len(w["shifts"]), "mass": w["mass"],
             "eps": w["eps"], "eps_shifts": w["eps_shifts"], "operator": "reference 1-D chain (inc/dirac_op.hpp:13-21)",
-            "partition": "1 slab" if gpus == 1 else "%d contiguous site slabs; halo sites and Gram blocks exchanged by P2P stores over NVLink from inside the kernels (NCCL only in the set-up)" % gpus,
+            "partition": "1 slab" if gpus == 1 else "%d contiguous site slabs; %s" % (gpus, EXCHANGE),
             "l2_policy": ("%d fields of %.0f MB each per GPU stream through every iteration (working set %s the"
                           " 126 MB L2); no explicit flush"
                           % (2 * len(w["shifts"]) + 2, 48.0 * w["N"] * w["V"] / gpus / 1e6,
@@ -171,6 +175,7 @@ def config_of(wname, w, gpus):
 
 
 def run_ours(args, w, wname):
+    global EXCHANGE
     import torch
 
     import blockcg_b200
@@ -208,7 +213,11 @@ def run_ours(args, w, wname):
         ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
         if not args.no_p2p:
             from blockcg_b200.distributed import exchange_ipc_handles
-            exchange_ipc_handles(dist, ctx, torch.device("cuda", local))
+            p2p_on = exchange_ipc_handles(dist, ctx, torch.device("cuda", local))
+            if not p2p_on:
+                EXCHANGE = "NCCL send/recv halo + all-reduce of the Gram blocks in the loop (peer mapping unavailable)"
+        else:
+            EXCHANGE = "NCCL send/recv halo + all-reduce of the Gram blocks in the loop (--no-p2p)"
     ctx.set_links(Ul, w["mass"])
 
     def barrier():

@@ -25,7 +25,7 @@ STATUS = {0: "BCG_OK", 1: "BCG_ERR_INVALID", 2: "BCG_ERR_CUDA", 3: "BCG_ERR_NOT_
 # every symbol include/blockcg_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "bcg_version", "bcg_supports_nrhs", "bcg_ctx_create", "bcg_ctx_destroy", "bcg_last_error",
-    "bcg_ctx_create_4d", "bcg_set_links_4d", "bcg_comm_get_unique_id", "bcg_comm_init", "bcg_comm_ipc_handle", "bcg_comm_ipc_open", "bcg_set_links", "bcg_field_alloc", "bcg_field_free",
+    "bcg_ctx_create_4d", "bcg_set_links_4d", "bcg_comm_get_unique_id", "bcg_comm_init", "bcg_comm_ipc_handle", "bcg_comm_ipc_open", "bcg_comm_ipc_disable", "bcg_set_links", "bcg_field_alloc", "bcg_field_free",
     "bcg_field_upload", "bcg_field_download", "bcg_field_zero", "bcg_field_copy", "bcg_op", "bcg_gram",
     "bcg_add", "bcg_add_scalar", "bcg_rescale_add", "bcg_trsm", "bcg_thinqr", "bcg_true_residual",
     "bcg_solve_bcg_dev", "bcg_solve_bcgrq_dev", "bcg_solve_sbcgrq_dev", "bcg_solve_bcg", "bcg_solve_bcgrq",
@@ -71,6 +71,7 @@ def load():
     lib.bcg_comm_init.argtypes = [C.c_void_p, C.c_void_p]
     lib.bcg_comm_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
     lib.bcg_comm_ipc_open.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bcg_comm_ipc_disable.argtypes = [C.c_void_p]
     lib.bcg_set_links.argtypes = [C.c_void_p, _dp, C.c_double]
     lib.bcg_set_links_4d.argtypes = [C.c_void_p, _dp, C.c_double]
     lib.bcg_ctx_create_4d.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
@@ -180,6 +181,10 @@ class Context:
         """handles: the ipc_handle() of every rank, concatenated in rank order."""
         buf = C.create_string_buffer(bytes(handles), len(handles))
         self._ck(self.lib.bcg_comm_ipc_open(self._h, buf))
+
+    def ipc_disable(self):
+        """Forget the peer mappings: the loop goes back to the NCCL exchange."""
+        self._ck(self.lib.bcg_comm_ipc_disable(self._h))
 
     def comm_init(self, uid):
         buf = C.create_string_buffer(bytes(uid), UNIQUE_ID_BYTES)

@@ -619,6 +619,16 @@ static int set_links(bcg_ctx* c, const double* links_host, double mass, int ndim
   c->links_set = true;
   return BCG_OK;
 }
+int bcg_comm_ipc_disable(bcg_ctx* c) {
+  if (!c) return BCG_ERR_INVALID;
+  c->p2p_ready = false;
+  if (c->graph.exec) {  // a captured loop may have baked the peer-memory path in
+    cudaGraphExecDestroy(c->graph.exec);
+    c->graph.exec = nullptr;
+  }
+  return BCG_OK;
+}
+
 int bcg_set_links(bcg_ctx* c, const double* links_host, double mass) { return set_links(c, links_host, mass, 1); }
 int bcg_set_links_4d(bcg_ctx* c, const double* links_host, double mass) { return set_links(c, links_host, mass, 4); }
 

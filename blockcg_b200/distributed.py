@@ -49,13 +49,34 @@ def exchange_ipc_handles(dist, ctx, device=None):
     this the iteration loop exchanges halos and Gram blocks with P2P stores over NVLink and
     contains no NCCL call."""
     import torch
-    mine = torch.frombuffer(bytearray(ctx.ipc_handle()), dtype=torch.uint8).clone()
+    from .capi import BcgError
+    ok = 1
+    try:
+        raw = ctx.ipc_handle()
+    except BcgError:
+        raw, ok = bytes(IPC_HANDLE_BYTES), 0
+    mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    flag = torch.tensor([ok], dtype=torch.int32)
     if device is not None:
-        mine = mine.to(device)
+        mine, flag = mine.to(device), flag.to(device)
     allh = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
     dist.all_gather(allh, mine)
-    ctx.ipc_open(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
-    dist.barrier()  # nobody pushes before everybody has mapped everybody
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 1:
+        try:
+            ctx.ipc_open(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+        except BcgError:
+            ok = 0
+    flag = torch.tensor([ok if int(flag.item()) == 1 else 0], dtype=torch.int32)
+    if device is not None:
+        flag = flag.to(device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # also the barrier: nobody pushes before everybody has mapped everybody
+    if int(flag.item()) != 1:
+        # some rank could not map its peers (no peer access / IPC forbidden): every rank stays on the
+        # NCCL path (halo send/recv + all-reduce), which needs nothing beyond bcg_comm_init
+        ctx.ipc_disable()
+        return False
+    return True
 
 
 def make_context(dist, V, N, max_shifts, device, U_global, mass, p2p=True):

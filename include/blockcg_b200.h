@@ -87,6 +87,8 @@ int bcg_comm_init(bcg_ctx* ctx, const void* id /* BCG_UNIQUE_ID_BYTES */);
  * N x N block into every peer's buffer themselves, the halo sites travel as P2P stores. */
 int bcg_comm_ipc_handle(bcg_ctx* ctx, void* handle_out /* BCG_IPC_HANDLE_BYTES */);
 int bcg_comm_ipc_open(bcg_ctx* ctx, const void* handles /* nranks * BCG_IPC_HANDLE_BYTES */);
+/* Back to the NCCL exchange (e.g. when some rank could not map its peers). */
+int bcg_comm_ipc_disable(bcg_ctx* ctx);
 
 /* ---- operator --------------------------------------------------------------------- */
 /* links_host: this rank's [v_local][3][3] links; halos (2 sites each side) are
