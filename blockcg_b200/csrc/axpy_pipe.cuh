@@ -45,7 +45,10 @@ template <int N, int TS, bool GRAM>
 __global__ void __launch_bounds__(AxpyPipeGeom<N, TS>::NT, 1)
 axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT,
                  const cd* __restrict__ M, long long V, cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl,
-                 const GramPeers peers) {
+                 const GramPeers peers, int reverse) {
+  // reverse != 0: tiles are visited from the high end of the field down.  The stencil that ran
+  // just before wrote T from site 0 upwards, so the top ~100 MB of T are still in L2; and the
+  // multishift update that runs next reads Q from site 0 upwards, i.e. the part written last.
   using Geo = AxpyPipeGeom<N, TS>;
   constexpr int NSPLIT = Geo::NSPLIT, JC = Geo::JC, SPW = Geo::SPW, NCW = Geo::NCW, SITE = Geo::SITE;
   constexpr int PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE, NS = Geo::NSTAGE;
@@ -79,7 +82,8 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const long long ntiles = (V + TS - 1) / TS;
   const int nmine = static_cast<int>(blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   auto tile_pair0 = [&](int i) {  // first site pair of this CTA's i-th tile
-    return static_cast<int>((static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * (TS / 2));
+    const long long tidx = static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x;
+    return static_cast<int>((reverse ? ntiles - 1 - tidx : tidx) * (TS / 2));
   };
   constexpr uint32_t TILE_BYTES = TILE * sizeof(cd);
 

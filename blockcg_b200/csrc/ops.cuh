@@ -1,5 +1,6 @@
 // Host-side launchers, one table per compiled N (see inst.cu / registry in capi.cu).
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "field_kernels.cuh"
@@ -101,6 +102,15 @@ inline int make_pair_map(CUtensorMap* m, const cd* base, int site, int box, long
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(cudaErrorInvalidValue);
+}
+
+// traversal order of the pipelined Q += T*M (see axpy_pipe_kernel); BCG_AXPY_REVERSE=0 for A/B runs
+inline int axpy_reverse() {
+  static const int v = [] {
+    const char* e = std::getenv("BCG_AXPY_REVERSE");
+    return e ? (e[0] != '0') : 1;
+  }();
+  return v;
 }
 
 #ifndef BCG_CHAIN_GMODE
@@ -305,9 +315,9 @@ struct Ops {
       if (e) return e;
       const int grid = clamp_grid((V + APIPE_TS - 1) / APIPE_TS, sms);
       if (gpart != nullptr)
-        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, gpart, ctrl, pe);
+        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
       else
-        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, nullptr, ctrl, pe);
+        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, nullptr, ctrl, pe, axpy_reverse());
       if (launches) ++*launches;
       e = err();
       return e ? e : (gpart != nullptr ? 1 : 0);
