@@ -48,6 +48,9 @@ WORKLOADS = {
     # configs[0]: the reference's README default (CPU-runnable)
     "sbcgrq_V1000_N12": dict(V=1000, N=12, mass=1e-3, eps=1e-10, eps_shifts=1e-15, shifts=BENCH_SHIFTS),
     "sbcgrq_16^4_N12": dict(V=16 ** 4, N=12, mass=1e-3, eps=1e-10, eps_shifts=1e-15, shifts=BENCH_SHIFTS),
+    # configs[3]: 48^3 x 96 sites on 2 / 4 / 8 GPUs (64 / 32 / 16 GB of fields per GPU); a full solve takes
+    # ~25 000 iterations of ~40 ms / n_gpus, so this one is meant to be run with --max-it
+    "sbcgrq_48^3x96_N12": dict(V=48 ** 3 * 96, N=12, mass=1e-3, eps=1e-10, eps_shifts=1e-15, shifts=BENCH_SHIFTS),
 }
 ITER_FILE = os.path.join(ROOT, "profiles", "bench_iterations.json")
 CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -60,6 +63,19 @@ def make_inputs(V, N, seed=1):
     U = rng.uniform(-1, 1, (V, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 3, 3))
     B = rng.uniform(-1, 1, (V, N, 3)) + 1j * rng.uniform(-1, 1, (V, N, 3))
     return U, B
+
+
+def make_inputs_slab(V, N, rank, world, chunks=8):
+    """Large volumes: the global problem is defined as `chunks` independently seeded pieces, each rank
+    generates only the pieces of its own slab (same global inputs for every world size dividing `chunks`)."""
+    assert chunks % world == 0 and V % chunks == 0
+    per, Vc = chunks // world, V // chunks
+    Us, Bs = [], []
+    for c in range(rank * per, (rank + 1) * per):
+        u, b = make_inputs(Vc, N, seed=1000 + c)
+        Us.append(u)
+        Bs.append(b)
+    return np.concatenate(Us), np.concatenate(Bs)
 
 
 class ClockSampler:
@@ -196,11 +212,18 @@ def run_ours(args, w, wname):
     if V % world:
         raise SystemExit("V=%d not divisible by %d ranks" % (V, world))
     Vl = V // world
-    U, B = make_inputs(V, N)
-    Ul = np.ascontiguousarray(U[rank * Vl:(rank + 1) * Vl])
+    big = V > 2 ** 21
+    if big:
+        Ul, Bl = make_inputs_slab(V, N, rank, world)
+        U = B = None
+    else:
+        U, B = make_inputs(V, N)
+        Ul = np.ascontiguousarray(U[rank * Vl:(rank + 1) * Vl])
+        Bl = B[rank * Vl:(rank + 1) * Vl]
     # pinned host buffers for the end-to-end path
     Bh = torch.empty((Vl, N, 3), dtype=torch.complex128).pin_memory()
-    Bh.numpy()[...] = B[rank * Vl:(rank + 1) * Vl]
+    Bh.numpy()[...] = Bl
+    del Bl
     Xh = [torch.empty((Vl, N, 3), dtype=torch.complex128).pin_memory() for _ in range(S)]
     Bn, Xn = Bh.numpy(), [x.numpy() for x in Xh]
 
@@ -301,7 +324,7 @@ def run_ours(args, w, wname):
         return
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not big:
         sec, it_cpu, kind, cores = reference_sample(w, U, B, args.cpu_iters)
         spi = sec / max(it_cpu, 1)
         cpu = {"value": spi * iters, "unit": "s", "cores": cores, "kind": kind,
