@@ -65,10 +65,15 @@ __device__ __noinline__ void sm_identity(cd* dst, int N) {
 __device__ __noinline__ void sm_mm(cd* C, const cd* A, const cd* B, int N) {
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
     BCG_IJ(e, i, j);
-    cd s = czero();
-#pragma unroll 4
-    for (int k = 0; k < N; ++k) cmac(s, A[i + N * k], B[k + N * j]);
-    C[e] = s;
+    cd s0 = czero(), s1 = czero();  // two interleaved partial sums halve the dependent chain
+    int k = 0;
+#pragma unroll 2
+    for (; k + 1 < N; k += 2) {
+      cmac(s0, A[i + N * k], B[k + N * j]);
+      cmac(s1, A[i + N * (k + 1)], B[k + 1 + N * j]);
+    }
+    if (k < N) cmac(s0, A[i + N * k], B[k + N * j]);
+    C[e] = cadd(s0, s1);
   }
   __syncthreads();
 }
@@ -76,10 +81,15 @@ __device__ __noinline__ void sm_mm(cd* C, const cd* A, const cd* B, int N) {
 __device__ __noinline__ void sm_mm_adj(cd* C, const cd* A, const cd* B, int N) {
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
     BCG_IJ(e, i, j);
-    cd s = czero();
-#pragma unroll 4
-    for (int k = 0; k < N; ++k) cmac(s, A[i + N * k], cconj(B[j + N * k]));
-    C[e] = s;
+    cd s0 = czero(), s1 = czero();
+    int k = 0;
+#pragma unroll 2
+    for (; k + 1 < N; k += 2) {
+      cmac(s0, A[i + N * k], cconj(B[j + N * k]));
+      cmac(s1, A[i + N * (k + 1)], cconj(B[j + N * (k + 1)]));
+    }
+    if (k < N) cmac(s0, A[i + N * k], cconj(B[j + N * k]));
+    C[e] = cadd(s0, s1);
   }
   __syncthreads();
 }
@@ -110,6 +120,14 @@ constexpr int kRedSlices = 8;
 __device__ __noinline__ void sm_reduce_gram(cd* G, const cd* __restrict__ gpart, int nparts, int N,
                                                cd* scratch) {
   const int nn = N * N, E = N * (N + 1) / 2;
+  if (nparts == 1) {  // the producing kernel has already reduced: copy the lower triangle, mirror it
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      BCG_IJ(e, i, j);
+      G[e] = (i >= j) ? gpart[e] : cconj(gpart[j + N * i]);
+    }
+    __syncthreads();
+    return;
+  }
   int nsl = static_cast<int>(blockDim.x) / E;
   nsl = nsl < 1 ? 1 : (nsl > kRedSlices ? kRedSlices : nsl);
   for (int w = threadIdx.x; w < E * nsl; w += blockDim.x) {
@@ -165,48 +183,54 @@ __device__ __noinline__ void sm_reduce_gram(cd* G, const cd* __restrict__ gpart,
   __syncthreads();
 }
 
-// Cholesky (lower, unblocked, left-looking as Eigen LLT.h:301-328) of the
-// Hermitian G, result returned as R = L^dag (upper, exactly zero below the
-// diagonal), as fields.hpp:142.  Returns -1 or the index of the first
-// non-positive pivot (uniform across the CTA).  Lw: N*N scratch.
+// Cholesky of the Hermitian G (real diagonal + lower triangle are read, as Eigen LLT.h:301-328),
+// returned as R = L^dag (upper, exactly zero below the diagonal), as fields.hpp:142.  Returns -1 or
+// the index of the first non-positive pivot (uniform across the CTA).  Lw: N*N scratch.
+// Right-looking, one matrix entry per thread and ONE barrier per column (the factorisation
+// ping-pongs between Lw and R): column k is scaled by 1/sqrt(pivot) and the trailing block gets
+// its rank-1 update in the same step; the reciprocal square root replaces sqrt + division.
+// (Eigen's unblocked LLT is left-looking: same factor, sums associated differently.)
 __device__ __noinline__ int sm_chol_upper(cd* R, const cd* G, cd* Lw, int N, int* s_info) {
-  sm_copy(Lw, G, N * N);
-  if (threadIdx.x < 32) {  // N dependent column steps: one warp, __syncwarp between them (cf. warp_lu_solve)
-    const int lane = threadIdx.x;
-    int info = -1;
-    for (int k = 0; k < N; ++k) {
-      // column k on and below the diagonal: s_i = L(i,k) - sum_j<k L(i,j) conj(L(k,j))
-      double x = 0.0;
-      for (int i = k + lane; i < N; i += 32) {
-        if (i == k) {
-          x = Lw[k + N * k].x;
-          for (int j = 0; j < k; ++j) x -= cabs2(Lw[k + N * j]);
-          Lw[k + N * k] = cmake(sqrt(x), 0.0);
+  const int nn = N * N;
+  sm_copy(Lw, G, nn);
+  cd* src = Lw;
+  cd* dst = R;
+  int info = -1;
+  for (int k = 0; k < N; ++k) {
+    const double x = src[k + N * k].x;
+    if (!(x > 0.0)) {
+      info = k;
+      break;
+    }
+    const double r = rsqrt(x), r2 = r * r;
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      BCG_IJ(e, i, j);
+      cd v = src[e];
+      if (i >= j && j >= k) {
+        if (j == k) {
+          v = (i == k) ? cmake(x * r, 0.0) : cscale(v, r);
         } else {
-          cd sacc = Lw[i + N * k];
-          for (int j = 0; j < k; ++j) cmsub(sacc, Lw[i + N * j], cconj(Lw[k + N * j]));
-          Lw[i + N * k] = sacc;
+          const cd aik = src[i + N * k], ajk = src[j + N * k];
+          cmsub(v, cscale(aik, r2), cconj(ajk));
         }
       }
-      x = __shfl_sync(0xffffffffu, x, 0);  // lane 0 owns the pivot (i == k  <=>  lane == 0)
-      __syncwarp();
-      if (!(x > 0.0)) {
-        info = k;
-        break;
-      }
-      const double d = Lw[k + N * k].x;
-      for (int i = k + 1 + lane; i < N; i += 32) Lw[i + N * k] = cscale(Lw[i + N * k], 1.0 / d);
-      __syncwarp();
+      dst[e] = v;
     }
-    if (lane == 0) *s_info = info;
+    __syncthreads();
+    cd* t = src;
+    src = dst;
+    dst = t;
   }
-  __syncthreads();
-  const int info = *s_info;
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+  if (src != Lw) {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) Lw[e] = src[e];
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     BCG_IJ(e, i, j);
     R[e] = (j >= i) ? cconj(Lw[j + N * i]) : czero();
   }
   __syncthreads();
+  if (threadIdx.x == 0) *s_info = info;
   return info;
 }
 
@@ -367,24 +391,19 @@ __device__ __noinline__ void sm_inverse(cd* A, cd* W, int N, int* piv, int* s_in
   cd* dst = W;
   for (int k = 0; k < N; ++k) {
     int br = k;
-    if (PIVOT) {  // largest |A(r,k)|, r >= k, first one on ties
-      double bv = -1.0;
+    if (PIVOT) {
+      // row of (nearly) largest |A(r,k)|, r >= k: the top 26 bits of |a|^2 (sign 0, exponent, 15
+      // mantissa bits) and the row number in the low 6 bits make one 32-bit key per candidate;
+      // one hardware max-reduction picks the winner.  Candidates that agree to 5 digits are
+      // equally good pivots; among those the highest row wins.
+      unsigned key = 0u;
       for (int r = k + lane; r < N; r += 32) {
-        const double a = cabs2(src[r + N * k]);
-        if (a > bv) {
-          bv = a;
-          br = r;
-        }
+        const unsigned kr = (static_cast<unsigned>(__double2hiint(cabs2(src[r + N * k]))) & ~63u) | static_cast<unsigned>(r);
+        key = kr > key ? kr : key;
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-        const int orow = __shfl_xor_sync(0xffffffffu, br, off);
-        if (ov > bv || (ov == bv && orow < br)) {
-          bv = ov;
-          br = orow;
-        }
-      }
+      key = __reduce_max_sync(0xffffffffu, key);
+      br = static_cast<int>(key & 63u);
+      if (br < k) br = k;  // all candidates zero
       if (tid == 0) piv[k] = br;
     }
     const cd pk = src[br + N * k];
@@ -497,6 +516,7 @@ __global__ void __launch_bounds__(kSmallThreads)
 gram_reduce_kernel(cd* __restrict__ out, const cd* __restrict__ gpart, int nparts, int N) {
   extern __shared__ __align__(16) unsigned char raw[];
   cd* G = reinterpret_cast<cd*>(raw);
+  sm_init_ij(N);
   sm_reduce_gram(G, gpart, nparts, N, G + N * N);
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) out[e] = G[e];
 }
@@ -587,37 +607,18 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   cd* alpha = s.mat[2];
   cd* delta = s.mat[3];
   cd* ad = s.mat[4];
-#ifdef BCG_DEBUG_TIMING
-  long long tt[6];
-  tt[0] = clock64();
-#endif
   const cd* gsrc = gpart;
   int nsrc = nparts;
   if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
   sm_reduce_gram(Ainv, gsrc, nsrc, N, s.mat[4]);
-#ifdef BCG_DEBUG_TIMING
-  tt[1] = clock64();
-#endif
   sm_copy(alpha, Ainv, nn);
-#ifdef BCG_DEBUG_TIMING
-  tt[2] = clock64();
-#endif
   sm_inverse<false>(alpha, lu, N, s.lw.rt, s.info);  // alpha = (P0^dag T)^-1, Hermitian positive definite
   if (threadIdx.x == 0 && *s.info >= 0) {  // singular P0^dag T: the operator is not positive definite
     ctrl->status = 3;
     ctrl->stop = 1;
   }
-#ifdef BCG_DEBUG_TIMING
-  tt[3] = clock64();
-#endif
   sm_copy(delta, mats + L.fixed(M_DELTA), nn);
   sm_mm(ad, alpha, delta, N);
-#ifdef BCG_DEBUG_TIMING
-  tt[4] = clock64();
-  if (threadIdx.x == 0 && iter <= 6)
-    printf("step_a it %d: reduce %lld copy %lld lu %lld mm %lld (clk)\n", iter, tt[1] - tt[0], tt[2] - tt[1],
-           tt[3] - tt[2], tt[4] - tt[3]);
-#endif
   cd* ainv_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     ainv_g[e] = Ainv[e];
