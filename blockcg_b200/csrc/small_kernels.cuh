@@ -43,8 +43,12 @@ struct MatLayout {
 // (row, column) of every linear matrix index, filled once per kernel: an integer division by
 // the run-time N costs more than a whole complex multiply-add chain of these little kernels.
 __shared__ int g_ij[1024];  // i | j << 16
+__shared__ int g_il[1024];  // shift_mat_index(N, i, j): position in the column-group-interleaved operand layout
 __device__ __forceinline__ void sm_init_ij(int N) {
-  for (int e = threadIdx.x; e < N * N; e += blockDim.x) g_ij[e] = (e % N) | ((e / N) << 16);
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+    g_ij[e] = (e % N) | ((e / N) << 16);
+    g_il[e] = shift_mat_index(N, e % N, e / N);
+  }
   __syncthreads();
 }
 #define BCG_IJ(e, i, j) const int ij_##i = g_ij[e]; const int i = ij_##i & 0xffff, j = ij_##i >> 16
@@ -409,7 +413,7 @@ __device__ __noinline__ void sm_inverse(cd* A, cd* W, int N, int* piv, int* s_in
     const cd pk = src[br + N * k];
     const double pa = cabs2(pk);
     if (tid == 0 && !(pa > 0.0)) *s_info = k;
-    const double pn = 1.0 / pa;
+    const double pn = __drcp_rn(pa);
     const cd rp = cmake(pk.x * pn, -pk.y * pn);  // 1 / pivot
     for (int e = tid; e < nn; e += blockDim.x) {
       BCG_IJ(e, i, j);
@@ -624,7 +628,7 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
     ainv_g[e] = Ainv[e];
     mats[L.fixed(M_ALPHA) + e] = alpha[e];
     mats[L.fixed(M_NEGALPHA) + e] = cmake(-alpha[e].x, -alpha[e].y);
-    mats[L.A(0) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = ad[e];
+    mats[L.A(0) + g_il[e]] = ad[e];
   }
 }
 
@@ -667,7 +671,7 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
       rho_g[e] = rho[e];
       mats[L.fixed(M_RHO_CUR) + e] = (i == j) ? cdiv(cmake(1.0, 0.0), rho[e]) : rho[e];
       mats[L.fixed(M_DELTA) + e] = dn[e];
-      mats[L.B(0) + shift_mat_index(N, i, j)] = cconj(rho[j + N * i]);
+      mats[L.B(0) + g_il[e]] = cconj(rho[j + N * i]);
     }
     if (threadIdx.x == 0) {
       double r = 0.0;
@@ -739,8 +743,8 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     mats[L.alpha_s(sh) + e] = t2[e];
     mats[L.beta_s(sh) + e] = beta[e];
-    mats[L.A(sh) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = t2[e];
-    mats[L.B(sh) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = t1[e];
+    mats[L.A(sh) + g_il[e]] = t2[e];
+    mats[L.B(sh) + g_il[e]] = t1[e];
   }
   if (threadIdx.x == 0) {
     double r = 0.0;
@@ -792,7 +796,7 @@ bcg_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpa
     const cd a = s.mat[1][e];
     mats[L.fixed(M_ALPHA) + e] = a;
     mats[L.fixed(M_NEGALPHA) + e] = cmake(-a.x, -a.y);
-    mats[L.A(0) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = a;
+    mats[L.A(0) + g_il[e]] = a;
   }
 }
 // B-step: r2_old = r2 ; r2 = R^dag R ; beta = LU(r2_old).solve(r2) ; residual ; B_0 = beta
@@ -817,7 +821,7 @@ bcg_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__
   sm_lu_solve(beta, r2old, s.lw, N);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     mats[L.fixed(M_R2) + e] = r2[e];
-    mats[L.B(0) + shift_mat_index(N, g_ij[e] & 0xffff, g_ij[e] >> 16)] = beta[e];
+    mats[L.B(0) + g_il[e]] = beta[e];
   }
   if (threadIdx.x == 0) {
     double r = 0.0;
