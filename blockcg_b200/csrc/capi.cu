@@ -822,7 +822,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
   r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
   if (p.kind == 1)
-    rq_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
+    rq_step_a_kernel<<<p.n_shifts, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   else
     bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   ++*launches;
@@ -916,6 +916,8 @@ int init_ctrl(bcg_ctx* c, int n_shifts, const double* sigma, double eps, double 
   Ctrl h;
   std::memset(&h, 0, sizeof h);
   h.n_unconv = n_shifts;
+  h.n_unconv_b = n_shifts;
+  h.iter_b = 0;
   h.n_shifts = n_shifts;
   h.max_it = max_it;
   h.eps = eps;

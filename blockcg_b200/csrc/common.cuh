@@ -77,6 +77,8 @@ struct Ctrl {
   int max_it;
   int n_shifts;
   int pad0;
+  int iter_b;     // copies of iter / n_unconv left by the B-step for the CTAs of the next A-step
+  int n_unconv_b;
   double eps;
   double eps_shifts;
   double residual;

@@ -573,9 +573,18 @@ rq_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm, 
   }
 }
 
-// A-step (after the stencil): alpha^-1 = herm(P0^dag T) ; alpha = LU-inverse ;
-// A_0 = alpha*delta (old delta!) ; -alpha.   (block_solvers.hpp:139-148)
-// Also: iteration bookkeeping (iter++, promote stop -> done, retire converged shifts).
+// A-step (after the stencil), one CTA per shift.
+//   every CTA : alpha^-1 = herm(P0^dag T) ; alpha = its inverse        (block_solvers.hpp:139-142)
+//   CTA 0     : A_0 = alpha*delta (old delta!) ; -alpha ; iteration bookkeeping (iter++, retire
+//               converged shifts)                                     (block_solvers.hpp:145-148)
+//   CTA s>=1  : beta_s and alpha_s of this iteration (block_solvers.hpp:163-168).  They depend on
+//               alpha, rho_old, alpha_inv_old and the old beta_s / alpha_s only -- not on the rho
+//               that the B-step will compute -- so this (the longest chain of the shifted
+//               coefficients: eight products and a pivoted inverse) runs here, next to the
+//               A-step's own inverse, instead of on the critical path of the B-step.
+// The CTAs may not race on the control block: all of them derive the iteration number and the
+// active-shift count from the copies (iter_b, n_unconv_b) the previous B-step left behind, and
+// only CTA 0 writes iter / n_unconv.
 __global__ void __launch_bounds__(kSmallThreads)
 rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpart, int nparts,
                  Ctrl* __restrict__ ctrl, const GramWait gw) {
@@ -585,50 +594,93 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
     if (threadIdx.x == 0) ctrl->done = 1;
     return;
   }
+  const int sh = blockIdx.x;
   extern __shared__ __align__(16) unsigned char raw[];
   const int N = L.N, nn = N * N;
   SmallSmem s;
   s.carve(raw, N);
   sm_init_ij(N);
-  const int iter = ctrl->iter + 1;
-  const int n_unconv_old = ctrl->n_unconv;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  const int iter = ctrl->iter_b + 1;
+  const int n_unconv_old = ctrl->n_unconv_b;
+  // shifts that passed the test in the previous iteration were still updated in it and drop out
+  // from this one on (block_solvers.hpp:161,175-181): every passing shift decrements the count,
+  // which always retires the highest index.
+  int n_unconv = n_unconv_old;
+  for (int q = 1; q < n_unconv_old; ++q)
+    if (ctrl->conv[q]) --n_unconv;
+  if (sh >= n_unconv && sh > 0) return;
+  if (sh == 0 && threadIdx.x == 0) {
     ctrl->iter = iter;
-    // shifts that passed the test in the previous iteration were still updated in
-    // it and drop out from this one on (block_solvers.hpp:161,175-181): every
-    // passing shift decrements the count, which always retires the highest index.
-    int n = n_unconv_old;
-    for (int sh = 1; sh < n_unconv_old; ++sh)
-      if (ctrl->conv[sh]) {
-        --n;
-        ctrl->conv[sh] = 0;
-      }
-    ctrl->n_unconv = n;
+    ctrl->n_unconv = n_unconv;
   }
   cd* Ainv = s.mat[0];
   cd* lu = s.mat[1];
   cd* alpha = s.mat[2];
-  cd* delta = s.mat[3];
-  cd* ad = s.mat[4];
   const cd* gsrc = gpart;
   int nsrc = nparts;
   if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
   sm_reduce_gram(Ainv, gsrc, nsrc, N, s.mat[4]);
   sm_copy(alpha, Ainv, nn);
   sm_inverse<false>(alpha, lu, N, s.lw.rt, s.info);  // alpha = (P0^dag T)^-1, Hermitian positive definite
-  if (threadIdx.x == 0 && *s.info >= 0) {  // singular P0^dag T: the operator is not positive definite
-    ctrl->status = 3;
-    ctrl->stop = 1;
+  if (sh == 0) {
+    cd* delta = s.mat[3];
+    cd* ad = s.mat[4];
+    if (threadIdx.x == 0 && *s.info >= 0) {  // singular P0^dag T: the operator is not positive definite
+      ctrl->status = 3;
+      ctrl->stop = 1;
+    }
+    sm_copy(delta, mats + L.fixed(M_DELTA), nn);
+    sm_mm(ad, alpha, delta, N);
+    cd* ainv_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0);
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      ainv_g[e] = Ainv[e];
+      mats[L.fixed(M_ALPHA) + e] = alpha[e];
+      mats[L.fixed(M_NEGALPHA) + e] = cmake(-alpha[e].x, -alpha[e].y);
+      mats[L.A(0) + g_il[e]] = ad[e];
+    }
+    return;
   }
-  sm_copy(delta, mats + L.fixed(M_DELTA), nn);
-  sm_mm(ad, alpha, delta, N);
-  cd* ainv_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0);
+  // ---- shifted coefficients that do not need the new rho ----
+  cd* rho_old = s.mat[4];
+  cd* ainv_old = s.mat[5];
+  cd* beta = s.mat[6];
+  cd* t1 = s.mat[7];
+  cd* t2 = s.mat[8];
+  cd* as = s.mat[9];
+  cd* G = s.mat[0];  // Ainv is not needed any more: scratch
+  const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    ainv_g[e] = Ainv[e];
-    mats[L.fixed(M_ALPHA) + e] = alpha[e];
-    mats[L.fixed(M_NEGALPHA) + e] = cmake(-alpha[e].x, -alpha[e].y);
-    mats[L.A(0) + g_il[e]] = ad[e];
+    rho_old[e] = rho_old_g[e];
+    ainv_old[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1) + e];
+    beta[e] = mats[L.beta_s(sh) + e];
+    as[e] = mats[L.alpha_s(sh) + e];
+  }
+  __syncthreads();
+  // beta_s_inv = I + (sigma_s - sigma_0) alpha + alpha rho_old alpha_inv_old (I - beta_s) rho_old^dag
+  sm_mm(t1, alpha, rho_old, N);
+  sm_mm(t2, t1, ainv_old, N);
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+    const double id = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? 1.0 : 0.0;
+    t1[e] = cmake(id - beta[e].x, -beta[e].y);
+  }
+  __syncthreads();
+  sm_mm(G, t2, t1, N);
+  sm_mm_adj(t1, G, rho_old, N);  // ... * rho_old^dag
+  const double ds = ctrl->sigma[sh] - ctrl->sigma[0];
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+    const double id = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? 1.0 : 0.0;
+    lu[e] = cmake((id + ds * alpha[e].x) + t1[e].x, (ds * alpha[e].y) + t1[e].y);
+  }
+  sm_copy(beta, lu, nn);
+  sm_inverse<true>(beta, lu, N, s.lw.rt, s.info);  // beta_s = beta_s_inv^-1 (general complex matrix)
+  // alpha_s = beta_s alpha rho_old alpha_inv_old alpha_s  (left to right)
+  sm_mm(t1, beta, alpha, N);
+  sm_mm(t2, t1, rho_old, N);
+  sm_mm(t1, t2, ainv_old, N);
+  sm_mm(t2, t1, as, N);  // new alpha_s
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+    mats[L.alpha_s(sh) + e] = t2[e];
+    mats[L.beta_s(sh) + e] = beta[e];
   }
 }
 
@@ -636,8 +688,8 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
 //   every CTA : G = herm(Q^dag Q) ; rho = chol(G)^dag            (fields.hpp:142)
 //   CTA 0     : delta = rho*delta ; residual ; stop test ; B_0 = rho^dag
 //               (block_solvers.hpp:152-158)
-//   CTA s>=1  : beta_s, alpha_s, shifted residual, A_s = alpha_s, B_s = beta_s rho^dag
-//               (block_solvers.hpp:163-181)
+//   CTA s>=1  : shifted residual rho alpha^-1 alpha_s, A_s = alpha_s, B_s = beta_s rho^dag with
+//               the alpha_s / beta_s the A-step has prepared   (block_solvers.hpp:169-181)
 __global__ void __launch_bounds__(kSmallThreads)
 rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ b_norm,
                  const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl, const GramWait gw) {
@@ -659,7 +711,6 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   sm_reduce_gram(G, gsrc, nsrc, N, s.mat[4]);
   const int info = sm_chol_upper(rho, G, t0, N, s.info);
   cd* rho_g = mats + L.fixed((iter & 1) ? M_RHO1 : M_RHO0);
-  const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
   if (sh == 0) {
     cd* delta = s.mat[3];
     cd* dn = s.mat[4];
@@ -669,7 +720,7 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
     for (int e = threadIdx.x; e < nn; e += blockDim.x) {
       BCG_IJ(e, i, j);
       rho_g[e] = rho[e];
-      mats[L.fixed(M_RHO_CUR) + e] = (i == j) ? cdiv(cmake(1.0, 0.0), rho[e]) : rho[e];
+      mats[L.fixed(M_RHO_CUR) + e] = (i == j) ? cmake(__drcp_rn(rho[e].x), 0.0) : rho[e];  // diagonal of chol: real > 0
       mats[L.fixed(M_DELTA) + e] = dn[e];
       mats[L.B(0) + g_il[e]] = cconj(rho[j + N * i]);
     }
@@ -681,8 +732,11 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
         if (v != v) nan = true;
         r = fmax(r, v);
       }
-      if (nan) r = nan ? (0.0 / 0.0) : r;
+      if (nan) r = 0.0 / 0.0;
       ctrl->residual = r;
+      // the copies the next A-step reads (its CTAs must not race with CTA 0's own updates)
+      ctrl->iter_b = iter;
+      ctrl->n_unconv_b = ctrl->n_unconv;
       // while (residual > eps && iter < max_iterations)  -- NaN ends the loop as in the reference
       if (!(r > ctrl->eps) || iter >= ctrl->max_it) ctrl->stop = 1;
       if (info >= 0) {
@@ -694,56 +748,24 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
     }
     return;
   }
-  // ---- shifted coefficients ----
-  cd* alpha = s.mat[3];
-  cd* rho_old = s.mat[4];
-  cd* ainv_old = s.mat[5];
+  // ---- shifted residual and the operands of the field update ----
   cd* beta = s.mat[6];
   cd* t1 = s.mat[7];
-  cd* t2 = s.mat[8];
   cd* as = s.mat[9];
   cd* ainv = s.mat[10];
-  cd* lu = s.mat[11];
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    alpha[e] = mats[L.fixed(M_ALPHA) + e];
-    rho_old[e] = rho_old_g[e];
-    ainv_old[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1) + e];
     ainv[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0) + e];
     beta[e] = mats[L.beta_s(sh) + e];
     as[e] = mats[L.alpha_s(sh) + e];
   }
   __syncthreads();
-  // beta_s_inv = I + (sigma_s - sigma_0) alpha + alpha rho_old alpha_inv_old (I - beta_s) rho_old^dag
-  sm_mm(t1, alpha, rho_old, N);
-  sm_mm(t2, t1, ainv_old, N);
-  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    const double id = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? 1.0 : 0.0;
-    t1[e] = cmake(id - beta[e].x, -beta[e].y);
-  }
-  __syncthreads();
-  sm_mm(G, t2, t1, N);           // G reused as scratch from here on
-  sm_mm_adj(t1, G, rho_old, N);  // ... * rho_old^dag
-  const double ds = ctrl->sigma[sh] - ctrl->sigma[0];
-  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    const double id = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? 1.0 : 0.0;
-    lu[e] = cmake((id + ds * alpha[e].x) + t1[e].x, (ds * alpha[e].y) + t1[e].y);
-  }
-  sm_copy(beta, lu, nn);
-  sm_inverse<true>(beta, lu, N, s.lw.rt, s.info);  // beta_s = beta_s_inv^-1 (general complex matrix)
-  // alpha_s = beta_s alpha rho_old alpha_inv_old alpha_s  (left to right)
-  sm_mm(t1, beta, alpha, N);
-  sm_mm(t2, t1, rho_old, N);
-  sm_mm(t1, t2, ainv_old, N);
-  sm_mm(t2, t1, as, N);  // new alpha_s
   // residual_shift = max_i || row_i(rho alpha_inv alpha_s) || / b_norm_i
   sm_mm(t1, rho, ainv, N);
-  sm_mm(G, t1, t2, N);
+  sm_mm(G, t1, as, N);
   sm_rownorms(s.vec, G, N);
   sm_mm_adj(t1, beta, rho, N);  // B_s = beta_s rho^dag
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    mats[L.alpha_s(sh) + e] = t2[e];
-    mats[L.beta_s(sh) + e] = beta[e];
-    mats[L.A(sh) + g_il[e]] = t2[e];
+    mats[L.A(sh) + g_il[e]] = as[e];
     mats[L.B(sh) + g_il[e]] = t1[e];
   }
   if (threadIdx.x == 0) {

@@ -3,6 +3,8 @@
 // inc/dirac_op.hpp:9-11).  op() runs the sm_100a block stencil through the C-ABI.
 #ifndef BLOCKCG_B200_HOST_DIRAC_OP_H
 #define BLOCKCG_B200_HOST_DIRAC_OP_H
+#include <array>
+
 #include "fields.hpp"
 
 class dirac_op {
@@ -19,14 +21,25 @@ class dirac_op {
   explicit dirac_op(int V, double mass = 0.1) : U(V), V(V), mass(mass) {
     for (int ix = 0; ix < V; ++ix) U[ix].setRandom();
   }
+  // 4-D extension (NOT in the reference): L0 x L1 x L2 x L3 periodic lattice, four links per site
+  // stored [site][mu]; D v[x] = 1/2 sum_mu (U_mu[x] v[x+mu] - U_mu[x-mu]^dag v[x-mu]), op = m^2 - D^2.
+  dirac_op(const std::array<int, 4>& L, double mass) : U(4 * static_cast<size_t>(L[0]) * L[1] * L[2] * L[3]),
+                                                       V(L[0] * L[1] * L[2] * L[3]), mass(mass), dims(L.begin(), L.end()) {
+    for (auto& u : U) u.setRandom();
+  }
+  std::vector<long long> dims;  // empty: the reference's 1-D chain
   const std::complex<double>* links() const { return U[0].data(); }
   std::complex<double>* links() { return U[0].data(); }
 
   // make this operator the one the (V, N) device context applies
   template <int N_rhs>
   bcg_ctx* bind(int n_shifts = 1) const {
+    bcg_host::current_dims() = dims;  // fields created from now on live on this operator's lattice
     bcg_ctx* c = bcg_host::context(V, N_rhs, n_shifts);
-    bcg_host::check(c, bcg_set_links(c, reinterpret_cast<const double*>(links()), mass), "bcg_set_links");
+    if (dims.size() == 4)
+      bcg_host::check(c, bcg_set_links_4d(c, reinterpret_cast<const double*>(links()), mass), "bcg_set_links_4d");
+    else
+      bcg_host::check(c, bcg_set_links(c, reinterpret_cast<const double*>(links()), mass), "bcg_set_links");
     return c;
   }
 

@@ -33,14 +33,22 @@ inline void check(bcg_ctx* c, int rc, const char* what) {
                              std::to_string(rc) + ")");
 }
 
-// one device context per (V, N); grown when more shifts are requested
+// Lattice geometry of the operator that fields are currently bound to: the reference's operator
+// is a 1-D chain of V sites (dims empty); the 4-D extension carries (L0, L1, L2, L3).
+inline std::vector<long long>& current_dims() {
+  static std::vector<long long> d;
+  return d;
+}
+
+// one device context per (V, N, geometry); grown when more shifts are requested
 inline bcg_ctx* context(int V, int N, int n_shifts = 1) {
   struct Entry {
     bcg_ctx* ctx;
     int S;
   };
-  static std::map<std::pair<int, int>, Entry> cache;
-  auto key = std::make_pair(V, N);
+  static std::map<std::pair<std::pair<int, int>, std::vector<long long>>, Entry> cache;
+  const std::vector<long long>& dims = current_dims();
+  auto key = std::make_pair(std::make_pair(V, N), dims);
   auto it = cache.find(key);
   if (it != cache.end() && it->second.S >= n_shifts) return it->second.ctx;
   if (it != cache.end()) {
@@ -48,7 +56,13 @@ inline bcg_ctx* context(int V, int N, int n_shifts = 1) {
     cache.erase(it);
   }
   bcg_ctx* c = nullptr;
-  int rc = bcg_ctx_create(&c, V, N, n_shifts, 0, 0, 1);
+  int rc;
+  if (dims.size() == 4) {
+    const int64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+    rc = bcg_ctx_create_4d(&c, d, N, n_shifts, 0, 0, 1);
+  } else {
+    rc = bcg_ctx_create(&c, V, N, n_shifts, 0, 0, 1);
+  }
   if (rc != BCG_OK) {
     std::string msg = c ? bcg_last_error(c) : "bcg_ctx_create failed";
     bcg_ctx_destroy(c);

@@ -83,5 +83,19 @@ int main() {
     for (int s = 0; s < n_shifts; ++s) check_block<N_rhs>("SBCGrQ", X[s], B, D, shifts[s], s);
   }
   std::printf("%s (%d assertions, %d failed)\n", failures ? "FAILED" : "All tests passed", checks, failures);
-  return failures;
+  const int ref_failures = failures;
+  {  // 4-D extension of the operator (not part of the reference's suite): SBCGrQ on a 6 x 4 x 4 x 8 lattice
+    checks = failures = 0;
+    const std::array<int, 4> L = {6, 4, 4, 8};
+    V = L[0] * L[1] * L[2] * L[3];
+    dirac_op D(L, mass);
+    block_fermion_field<N_rhs> B(V);
+    std::vector<block_fermion_field<N_rhs>> X(n_shifts, B);
+    B.setRandom();
+    int it = SBCGrQ(X, B, D, shifts, stopping_criterion);
+    std::printf("4-D SBCGrQ: %d iterations\n", it);
+    for (int s = 0; s < n_shifts; ++s) check_block<N_rhs>("SBCGrQ4", X[s], B, D, shifts[s], s);
+    std::printf("4-D extension: %s (%d assertions, %d failed)\n", failures ? "FAILED" : "passed", checks, failures);
+  }
+  return ref_failures + failures;
 }

@@ -24,7 +24,8 @@ def test_reference_regression_suite():
     out = subprocess.run([_binary("test_solvers")], capture_output=True, text=True, timeout=600)
     print(out.stdout[-2000:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "27" in out.stdout  # 1 + 5 + 3 + 3 + 15 assertions, as in the reference
+    assert "All tests passed (27 assertions" in out.stdout  # 1 + 5 + 3 + 3 + 15, as in the reference
+    assert "4-D extension: passed (15 assertions" in out.stdout  # SBCGrQ on a 4-D lattice through dirac_op(L, mass)
 
 
 def test_benchmark_program_readme_config():
