@@ -391,6 +391,10 @@ int upload_mat(bcg_ctx* c, int slot, const double* host, int staging) {
 }
 
 int ensure_work(bcg_ctx* c, int n_shifts) {
+  if (c->ndim == 4 && c->work_D < 0) {  // intermediate field of the two-sweep apply: never allocate inside a capture
+    int r = field_alloc(c, &c->work_D);
+    if (r) return r;
+  }
   if (c->work_T < 0) {
     int r = field_alloc(c, &c->work_T);
     if (r) return r;

@@ -577,11 +577,12 @@ rq_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm, 
 //   every CTA : alpha^-1 = herm(P0^dag T) ; alpha = its inverse        (block_solvers.hpp:139-142)
 //   CTA 0     : A_0 = alpha*delta (old delta!) ; -alpha ; iteration bookkeeping (iter++, retire
 //               converged shifts)                                     (block_solvers.hpp:145-148)
-//   CTA s>=1  : beta_s and alpha_s of this iteration (block_solvers.hpp:163-168).  They depend on
-//               alpha, rho_old, alpha_inv_old and the old beta_s / alpha_s only -- not on the rho
-//               that the B-step will compute -- so this (the longest chain of the shifted
-//               coefficients: eight products and a pivoted inverse) runs here, next to the
-//               A-step's own inverse, instead of on the critical path of the B-step.
+//   CTA s>=1  : beta_s of this iteration (block_solvers.hpp:163-166).  It depends on alpha, rho_old,
+//               alpha_inv_old and the old beta_s only -- not on the rho that the B-step will
+//               compute -- so this half of the shifted coefficients (five products and a pivoted
+//               inverse) runs here, next to the A-step's own inverse; the B-step does the other
+//               half (alpha_s, residual, operands).  Each kernel is as long as its longest CTA, so
+//               the chain is split where the two kernels come out about equal.
 // The CTAs may not race on the control block: all of them derive the iteration number and the
 // active-shift count from the copies (iter_b, n_unconv_b) the previous B-step left behind, and
 // only CTA 0 writes iter / n_unconv.
@@ -646,14 +647,12 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   cd* beta = s.mat[6];
   cd* t1 = s.mat[7];
   cd* t2 = s.mat[8];
-  cd* as = s.mat[9];
   cd* G = s.mat[0];  // Ainv is not needed any more: scratch
   const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     rho_old[e] = rho_old_g[e];
     ainv_old[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1) + e];
     beta[e] = mats[L.beta_s(sh) + e];
-    as[e] = mats[L.alpha_s(sh) + e];
   }
   __syncthreads();
   // beta_s_inv = I + (sigma_s - sigma_0) alpha + alpha rho_old alpha_inv_old (I - beta_s) rho_old^dag
@@ -673,23 +672,15 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   }
   sm_copy(beta, lu, nn);
   sm_inverse<true>(beta, lu, N, s.lw.rt, s.info);  // beta_s = beta_s_inv^-1 (general complex matrix)
-  // alpha_s = beta_s alpha rho_old alpha_inv_old alpha_s  (left to right)
-  sm_mm(t1, beta, alpha, N);
-  sm_mm(t2, t1, rho_old, N);
-  sm_mm(t1, t2, ainv_old, N);
-  sm_mm(t2, t1, as, N);  // new alpha_s
-  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    mats[L.alpha_s(sh) + e] = t2[e];
-    mats[L.beta_s(sh) + e] = beta[e];
-  }
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) mats[L.beta_s(sh) + e] = beta[e];
 }
 
 // B-step (after Q -= T alpha and its Gram): one CTA per shift.
 //   every CTA : G = herm(Q^dag Q) ; rho = chol(G)^dag            (fields.hpp:142)
 //   CTA 0     : delta = rho*delta ; residual ; stop test ; B_0 = rho^dag
 //               (block_solvers.hpp:152-158)
-//   CTA s>=1  : shifted residual rho alpha^-1 alpha_s, A_s = alpha_s, B_s = beta_s rho^dag with
-//               the alpha_s / beta_s the A-step has prepared   (block_solvers.hpp:169-181)
+//   CTA s>=1  : alpha_s (with the beta_s the A-step has prepared), shifted residual
+//               rho alpha^-1 alpha_s, A_s = alpha_s, B_s = beta_s rho^dag   (block_solvers.hpp:167-181)
 __global__ void __launch_bounds__(kSmallThreads)
 rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ b_norm,
                  const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl, const GramWait gw) {
@@ -748,24 +739,38 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
     }
     return;
   }
-  // ---- shifted residual and the operands of the field update ----
+  // ---- alpha_s, shifted residual and the operands of the field update ----
+  cd* alpha = s.mat[3];
+  cd* rho_old = s.mat[4];
+  cd* ainv_old = s.mat[5];
   cd* beta = s.mat[6];
   cd* t1 = s.mat[7];
+  cd* t2 = s.mat[8];
   cd* as = s.mat[9];
   cd* ainv = s.mat[10];
+  const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+    alpha[e] = mats[L.fixed(M_ALPHA) + e];
+    rho_old[e] = rho_old_g[e];
+    ainv_old[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1) + e];
     ainv[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0) + e];
-    beta[e] = mats[L.beta_s(sh) + e];
+    beta[e] = mats[L.beta_s(sh) + e];  // this iteration's beta_s, from the A-step
     as[e] = mats[L.alpha_s(sh) + e];
   }
   __syncthreads();
+  // alpha_s = beta_s alpha rho_old alpha_inv_old alpha_s  (left to right)
+  sm_mm(t1, beta, alpha, N);
+  sm_mm(t2, t1, rho_old, N);
+  sm_mm(t1, t2, ainv_old, N);
+  sm_mm(t2, t1, as, N);  // new alpha_s
   // residual_shift = max_i || row_i(rho alpha_inv alpha_s) || / b_norm_i
   sm_mm(t1, rho, ainv, N);
-  sm_mm(G, t1, as, N);
+  sm_mm(G, t1, t2, N);
   sm_rownorms(s.vec, G, N);
   sm_mm_adj(t1, beta, rho, N);  // B_s = beta_s rho^dag
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    mats[L.A(sh) + g_il[e]] = as[e];
+    mats[L.alpha_s(sh) + e] = t2[e];
+    mats[L.A(sh) + g_il[e]] = t2[e];
     mats[L.B(sh) + g_il[e]] = t1[e];
   }
   if (threadIdx.x == 0) {
