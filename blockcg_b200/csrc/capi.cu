@@ -606,6 +606,10 @@ int bcg_comm_ipc_open(bcg_ctx* c, const void* handles) {
     c->p2p_peer[r] = static_cast<unsigned char*>(ptr);
   }
   c->p2p_ready = true;
+  if (c->graph.exec) {  // a loop captured earlier baked the NCCL exchange in
+    cudaGraphExecDestroy(c->graph.exec);
+    c->graph.exec = nullptr;
+  }
   return BCG_OK;
 }
 
