@@ -18,10 +18,14 @@
 //                       sub-chains (contiguous site ranges); every tile advances each of
 //                       them by W sites.
 //   4 Gram warps      : a quarter of the lower triangle of P^dag T each (GramPart), over the
-//                       rows of the finished tile, accumulated in registers over the whole kernel, one partial N x N
-//                       block per CTA at the end (fixed order => deterministic).
-//   1 loader warp     : cp.async.bulk (SASS UBLKCP) of the P / U windows, PF tiles ahead.
-//   1 storer warp     : bulk stores of the T windows.
+//                       rows of the finished tile, accumulated in registers over the whole
+//                       kernel; at the end the CTA's block is reduced across CTAs (group of 8,
+//                       then grid; always the last arriver adds, in index order => deterministic)
+//                       and, in a slab decomposition, stored into every peer's buffer over NVLink.
+//   1 loader lane     : three tensor-map TMA copies per tile (SASS UTMALDG): the P windows and
+//                       link windows of all K sub-chains as boxes of a [window][tile][chain]
+//                       view, up to three tiles ahead.
+//   1 storer lane     : one tensor store (UTMASTG) of the T windows per tile.
 // Hand-off is by mbarriers only (inb: TMA -> stencil, ofull: stencil -> Gram + storer,
 // gdone: Gram -> loader + stencil, sdone: storer -> stencil); no __syncthreads in the loop.
 #pragma once
