@@ -258,6 +258,26 @@ def test_full_size_properties(bcg, oracle):
             assert rel(ctx.download(xs[s]), Xo[s]) < 1e-10
 
 
+def test_error_paths_4d_and_peer_api(bcg):
+    with bcg.Context(0, 3, dims=(4, 2, 2, 2)) as ctx:
+        assert ctx.V == 32
+        with pytest.raises(bcg.BcgError):  # a 4-D context wants [V][4][3][3] links through bcg_set_links_4d
+            ctx._ck(ctx.lib.bcg_set_links(ctx._h, np.zeros((32, 3, 3), np.complex128).ctypes.data_as(bcg.capi._dp), 0.5))
+        ctx.set_links(np.zeros((32, 4, 3, 3), np.complex128), 0.5)
+        hb, hx = ctx.field(np.ones((32, 3, 3), np.complex128)), ctx.field()
+        ctx.op(hx, hb)  # zero links: op = m^2
+        assert np.allclose(ctx.download(hx), 0.25)
+    with pytest.raises(bcg.BcgError):
+        bcg.Context(0, 3, dims=(4, 0, 2, 2))
+    with bcg.Context(16, 3) as ctx:
+        with pytest.raises(bcg.BcgError):  # peers can only be opened after this rank's own buffer exists
+            ctx.ipc_open(bytes(64))
+        h = ctx.ipc_handle()
+        assert len(h) == 64
+        ctx.ipc_open(h)  # one rank: its own buffer
+        ctx.ipc_disable()
+
+
 def test_error_paths(bcg):
     with pytest.raises(bcg.BcgError):
         bcg.Context(16, 5)  # N not compiled in
