@@ -644,7 +644,9 @@ struct ShiftGeom {
   static constexpr int STAGE_ELEMS = (2 * TILE + 2 * N * N + 7) / 8 * 8;
   static constexpr int NSTAGE = 2;
   static constexpr size_t SMEM_BYTES = sizeof(cd) * NSTAGE * STAGE_ELEMS + 64;
-  static constexpr int MAXREG = (2 * SMEM_BYTES <= 220 * 1024) ? 128 : 232;
+  // registers are allocated per 4 warps: two resident CTAs of <= 8 warp slots each may use 128 per
+  // thread, one CTA of <= 8 warps 232, one of 9..12 warps 168
+  static constexpr int MAXREG = (2 * SMEM_BYTES <= 220 * 1024 && NT <= 256) ? 128 : (NT <= 256 ? 232 : 168);
 };
 
 // tensor maps of the fields one multishift launch touches (kernel parameter, __grid_constant__)

