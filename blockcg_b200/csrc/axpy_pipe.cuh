@@ -169,7 +169,7 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
     for (int j = 0; j < JC; ++j)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[c][j] = sQ[3 * (h * JC + j) + c];
+      for (int c = 0; c < 3; ++c) acc[c][j] = czero();
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const cd p0 = sT[3 * k], p1 = sT[3 * k + 1], p2 = sT[3 * k + 2];
@@ -184,7 +184,8 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
     for (int j = 0; j < JC; ++j)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) sQ[3 * (h * JC + j) + c] = acc[c][j];
+      for (int c = 0; c < 3; ++c)  // product first, then one addition (reference: tmp = rhs * M; this += tmp)
+        sQ[3 * (h * JC + j) + c] = cadd(sQ[3 * (h * JC + j) + c], acc[c][j]);
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {

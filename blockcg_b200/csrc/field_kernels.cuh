@@ -425,10 +425,14 @@ axpy_gram_kernel(cd* __restrict__ Q, const cd* __restrict__ T, const cd* __restr
     const int rows_here = static_cast<int>(min(static_cast<long long>(NT), nrows - tile * NT));
     if (row < nrows) {
       const long long rb = row_base_of(row, N);
-      cd t[N], q[N];
+      cd t[N], q[N], dq[N];
       row_load<N>(T, rb, t);
       row_load<N>(Q, rb, q);
-      row_mm_acc<N>(q, t, sM);
+#pragma unroll
+      for (int j = 0; j < N; ++j) dq[j] = czero();
+      row_mm_acc<N>(dq, t, sM);
+#pragma unroll
+      for (int j = 0; j < N; ++j) q[j] = cadd(q[j], dq[j]);  // product first, then one addition (fields.hpp:74)
       row_store<N>(Q, rb, q);
       if (GRAM) {
         const int lb = (tid / 3) * (3 * N) + (tid % 3);
@@ -585,9 +589,13 @@ shift_update_kernel(cd* __restrict__ Q, ShiftPtrs fp, const cd* __restrict__ Rm,
         cd p[N];
         row_load<N>(fp.P[s], rb, p);
         {
-          cd x[N];
+          cd x[N], dx[N];
           row_load<N>(fp.X[s], rb, x);
-          row_mm_acc_il<N>(x, p, sAb);
+#pragma unroll
+          for (int j = 0; j < N; ++j) dx[j] = czero();
+          row_mm_acc_il<N>(dx, p, sAb);
+#pragma unroll
+          for (int j = 0; j < N; ++j) x[j] = cadd(x[j], dx[j]);  // product first, one addition into X (fields.hpp:74)
           row_store<N>(fp.X[s], rb, x);
         }
         {
@@ -798,7 +806,7 @@ shift_pipe_kernel(const __grid_constant__ ShiftMaps maps, const cd* __restrict__
 #pragma unroll
         for (int j = 0; j < JC; ++j)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) acc[c][j] = sX[3 * (h * JC + j) + c];
+          for (int c = 0; c < 3; ++c) acc[c][j] = czero();
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           const cd p0 = sP[3 * k], p1 = sP[3 * k + 1], p2 = sP[3 * k + 2];
@@ -810,10 +818,13 @@ shift_pipe_kernel(const __grid_constant__ ShiftMaps maps, const cd* __restrict__
             cmac(acc[2][j], p2, m);
           }
         }
+        // the product first, ONE addition into X last (as the reference: tmp = rhs * M; this += tmp,
+        // fields.hpp:74): late in a solve |X| >> |increment|, and accumulating the N terms straight into
+        // X would round N times at the size of X -- measured as a 5x higher true-residual floor
 #pragma unroll
         for (int j = 0; j < JC; ++j)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) sX[3 * (h * JC + j) + c] = acc[c][j];
+          for (int c = 0; c < 3; ++c) sX[3 * (h * JC + j) + c] = cadd(sX[3 * (h * JC + j) + c], acc[c][j]);
         // ---- P_s <- P_s B_s + Q ----
 #pragma unroll
         for (int j = 0; j < JC; ++j)

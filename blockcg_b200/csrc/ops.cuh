@@ -113,6 +113,16 @@ inline int axpy_reverse() {
   return v;
 }
 
+// diagnostic: BCG_FORCE_V1 = bit mask of kernels to run in their first-generation form
+// (1 stencil, 2 Q += T*M, 4 multishift update) -- for A/B comparisons of accuracy and speed
+inline int force_v1() {
+  static const int v = [] {
+    const char* e = std::getenv("BCG_FORCE_V1");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v;
+}
+
 #ifndef BCG_CHAIN_GMODE
 #define BCG_CHAIN_GMODE 1
 #endif
@@ -261,6 +271,7 @@ struct Ops {
                    cd* gpart, const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers) {
     GramPeers pe;
     if (peers) pe = *peers; else std::memset(&pe, 0, sizeof pe);
+    if (force_v1() & 1) return dirac_v1(st, in, out, U, V, m2, sigma, gpart, ctrl, sms, launches);
     if constexpr (CHAIN) {
       prepare(sms);
       const ChainPlan pl = chain_plan(V, sms);
@@ -308,6 +319,7 @@ struct Ops {
                        const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers) {
     GramPeers pe;
     if (peers) pe = *peers; else std::memset(&pe, 0, sizeof pe);
+    if (force_v1() & 2) return axpy_gram_v1(st, Q, T, M, V, gpart, ctrl, sms, launches);
     if constexpr (APIPE) {
       prepare(sms);
       alignas(64) CUtensorMap tmQ, tmT;
@@ -367,6 +379,7 @@ struct Ops {
                           long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl, int sms,
                           int* launches) {
     prepare(sms);
+    if (force_v1() & 4) return shift_update_direct(st, Q, fp, Rm, A, B, V, do_backsub, n_active_fixed, ctrl, sms, launches);
     if constexpr (PIPE_OK) {
       const int grid = clamp_grid((V + SHIFT_TS - 1) / SHIFT_TS, caps().pipe);
       // tensor maps of every field the launch may touch (n_active is only known on the device)
