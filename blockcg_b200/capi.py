@@ -26,7 +26,7 @@ STATUS = {0: "BCG_OK", 1: "BCG_ERR_INVALID", 2: "BCG_ERR_CUDA", 3: "BCG_ERR_NOT_
 EXPORTS = [
     "bcg_version", "bcg_supports_nrhs", "bcg_ctx_create", "bcg_ctx_destroy", "bcg_last_error",
     "bcg_ctx_create_4d", "bcg_set_links_4d", "bcg_comm_get_unique_id", "bcg_comm_init", "bcg_comm_ipc_handle", "bcg_comm_ipc_open", "bcg_comm_ipc_disable", "bcg_set_links", "bcg_field_alloc", "bcg_field_free",
-    "bcg_field_upload", "bcg_field_download", "bcg_field_zero", "bcg_field_copy", "bcg_op", "bcg_gram",
+    "bcg_field_upload", "bcg_field_download", "bcg_field_random", "bcg_set_links_random", "bcg_field_zero", "bcg_field_copy", "bcg_op", "bcg_gram",
     "bcg_add", "bcg_add_scalar", "bcg_rescale_add", "bcg_trsm", "bcg_thinqr", "bcg_true_residual",
     "bcg_solve_bcg_dev", "bcg_solve_bcgrq_dev", "bcg_solve_sbcgrq_dev", "bcg_solve_bcg", "bcg_solve_bcgrq",
     "bcg_solve_sbcgrq", "bcg_bench_kernel",
@@ -81,6 +81,8 @@ def load():
     lib.bcg_field_upload.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.bcg_field_download.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.bcg_field_zero.argtypes = [C.c_void_p, C.c_int]
+    lib.bcg_field_random.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+    lib.bcg_set_links_random.argtypes = [C.c_void_p, C.c_uint64, C.c_double]
     lib.bcg_field_copy.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bcg_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, _dp]
     lib.bcg_gram.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
@@ -199,6 +201,13 @@ class Context:
             return
         assert U.shape == (self.V, 3, 3), U.shape
         self._ck(self.lib.bcg_set_links(self._h, _dptr(U), float(mass)))
+
+    def set_links_random(self, seed, mass):
+        """Links drawn on the device (uniform in [-1, 1), counter-based: independent of the rank count)."""
+        self._ck(self.lib.bcg_set_links_random(self._h, int(seed), float(mass)))
+
+    def field_random(self, h, seed):
+        self._ck(self.lib.bcg_field_random(self._h, h, int(seed)))
 
     def field(self, data=None):
         h = C.c_int(-1)

@@ -640,6 +640,33 @@ int bcg_comm_ipc_disable(bcg_ctx* c) {
 int bcg_set_links(bcg_ctx* c, const double* links_host, double mass) { return set_links(c, links_host, mass, 1); }
 int bcg_set_links_4d(bcg_ctx* c, const double* links_host, double mass) { return set_links(c, links_host, mass, 4); }
 
+// ---- inputs generated in place (volumes too large to stage through the host) -----------------
+static int fill_uniform(bcg_ctx* c, cd* dst, int site, uint64_t seed, uint64_t stream) {
+  const long long n = 2LL * c->V * site;  // doubles held by this rank
+  const unsigned long long first = 2ULL * static_cast<unsigned long long>(c->rank) * c->V * site;
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 16));
+  fill_uniform_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<double*>(dst), n, first, seed, stream);
+  CU(cudaGetLastError());
+  return BCG_OK;
+}
+int bcg_field_random(bcg_ctx* c, int h, uint64_t seed) {
+  if (!c || !valid(c, h)) return fail(c, BCG_ERR_INVALID, "bad field handle %d", h);
+  CU(cudaSetDevice(c->device));
+  return fill_uniform(c, fptr(c, h), site_elems(c), seed, /*stream*/ 1);
+}
+int bcg_set_links_random(bcg_ctx* c, uint64_t seed, double mass) {
+  if (!c) return BCG_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  int r = fill_uniform(c, uptr(c), c->links_site, seed, /*stream*/ 0);
+  if (r) return r;
+  r = halo_refresh(c, uptr(c), c->links_site, nullptr, nullptr);
+  if (r) return r;
+  CU(cudaStreamSynchronize(c->stream));
+  c->mass = mass;
+  c->links_set = true;
+  return BCG_OK;
+}
+
 int bcg_field_alloc(bcg_ctx* c, int* h) {
   if (!c || !h) return fail(c, BCG_ERR_INVALID, "null argument");
   CU(cudaSetDevice(c->device));

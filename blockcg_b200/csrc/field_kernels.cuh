@@ -856,6 +856,26 @@ shift_pipe_kernel(const __grid_constant__ ShiftMaps maps, const cd* __restrict__
   }
 }
 
+// Counter-based uniform numbers in [-1, 1) for inputs generated in place (the reference fills
+// its links and sources with Eigen's setRandom, i.e. -1 + 2*rand()/RAND_MAX: inc/dirac_op.hpp:24-32,
+// benchmark.cpp:60-62 -- the same distribution, not the same stream: libc's rand() is sequential).
+// Double number `first + i` of the GLOBAL array gets mix(seed, stream, first + i), so a field does
+// not depend on how many ranks it is split over.  mix = the SplitMix64 finaliser.
+__host__ __device__ inline double counter_uniform(unsigned long long seed, unsigned long long stream,
+                                                  unsigned long long index) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (index + 1) + 0xD1B54A32D192ED03ull * stream;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<double>(z >> 11) * 0x1.0p-52 - 1.0;  // exact: a multiple of 2^-52
+}
+static __global__ void fill_uniform_kernel(double* __restrict__ dst, long long n, unsigned long long first,
+                                           unsigned long long seed, unsigned long long stream) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = counter_uniform(seed, stream, first + static_cast<unsigned long long>(i));
+}
+
 // Halo refresh for one rank: slots -H..-1 and V..V+H-1 <- periodic images (any V >= 1).
 // `site` = complex numbers per site (3N for fields, 9 or 36 for links); H = 2 for the 1-D
 // chain, one x3-slice for the 4-D operator.

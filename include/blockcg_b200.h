@@ -98,11 +98,21 @@ int bcg_set_links(bcg_ctx* ctx, const double* links_host, double mass);
  * D v[x] = 1/2 sum_mu ( U_mu[x] v[x+mu] - U_mu[x-mu]^dag v[x-mu] ), operator m^2 - D^2. */
 int bcg_set_links_4d(bcg_ctx* ctx, const double* links_host, double mass);
 
+/* Links drawn in place on the device, uniform in [-1, 1) per real/imaginary part -- the
+ * distribution of the reference's dirac_op constructor (inc/dirac_op.hpp:24-32, Eigen setRandom),
+ * from a counter-based generator instead of libc rand(): double number k of the GLOBAL
+ * [V][3][3] (or [V][4][3][3]) array is a fixed function of (seed, k), whatever the number of ranks.
+ * For volumes too large to stage through the host. */
+int bcg_set_links_random(bcg_ctx* ctx, uint64_t seed, double mass);
+
 /* ---- device-resident fields --------------------------------------------------------- */
 int bcg_field_alloc(bcg_ctx* ctx, int* handle_out);
 int bcg_field_free(bcg_ctx* ctx, int handle);
 int bcg_field_upload(bcg_ctx* ctx, int handle, const double* host);   /* [v_local][N][3] */
 int bcg_field_download(bcg_ctx* ctx, int handle, double* host);
+/* The same generator for a field (reference: block_fermion_field setRandom in benchmark.cpp:60-62);
+ * a different stream from the links, so equal seeds do not correlate them. */
+int bcg_field_random(bcg_ctx* ctx, int handle, uint64_t seed);
 int bcg_field_zero(bcg_ctx* ctx, int handle);
 int bcg_field_copy(bcg_ctx* ctx, int dst, int src);
 

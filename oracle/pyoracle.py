@@ -263,3 +263,18 @@ class RefShim:
         it = self._f("ref_SBCGrQ")(C.c_int(V), C.c_double(mass), _p(U), _p(B), _p(X), _p(sig), C.c_int(S),
                                    C.c_double(eps), C.c_double(eps_shifts), C.c_int(max_it), C.byref(sec))
         return X, it, sec.value
+
+
+def counter_uniform(seed, stream, first, n):
+    """numpy restatement of the device input generator (blockcg_b200/csrc/field_kernels.cuh,
+    counter_uniform): doubles number first .. first+n-1 of the global array, uniform in [-1, 1) --
+    the distribution of the reference's setRandom (inc/dirac_op.hpp:24-32, benchmark.cpp:60-62)."""
+    m = (1 << 64) - 1
+    idx = np.arange(first + 1, first + n + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & m) + np.uint64(0x9E3779B97F4A7C15) * idx + np.uint64((0xD1B54A32D192ED03 * stream) & m)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    return (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -52 - 1.0
+

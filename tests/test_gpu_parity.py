@@ -258,6 +258,43 @@ def test_full_size_properties(bcg, oracle):
             assert rel(ctx.download(xs[s]), Xo[s]) < 1e-10
 
 
+def test_inputs_generated_on_device(bcg, oracle):
+    """bcg_field_random / bcg_set_links_random against the numpy restatement, bit for bit; a slab
+    is a slice of the global array; a solve on generated inputs meets the reference's residual rule."""
+    import oracle.pyoracle as ora
+    V, N, mass, eps = 640, 4, 0.3, 1e-10
+    with bcg.Context(V, N, max_shifts=2) as ctx:
+        hb, hx, hy = ctx.field(), ctx.field(), ctx.field()
+        ctx.field_random(hb, 11)
+        B = ctx.download(hb)
+        want = ora.counter_uniform(11, 1, 0, 2 * V * N * 3).view(np.complex128).reshape(V, N, 3)
+        assert np.array_equal(B, want)
+        ctx.set_links_random(11, mass)
+        U = ora.counter_uniform(11, 0, 0, 2 * V * 9).view(np.complex128).reshape(V, 3, 3)
+        ctx.op(hx, hb, 0.25)
+        assert rel(ctx.download(hx), oracle.op(U, B, mass, 0.25)) < 1e-13
+        ctx.solve_sbcgrq_dev([hx, hy], hb, [0.0, 0.1], eps, 1e-15)
+        for h, sg in ((hx, 0.0), (hy, 0.1)):
+            assert oracle.true_residual(U, B, ctx.download(h), mass, sg).max() < 2 * eps
+    with bcg.Context(V // 2, N, rank=1, nranks=2) as ctx:  # no communicator needed to fill a field
+        h = ctx.field()
+        ctx.field_random(h, 11)
+        assert np.array_equal(ctx.download(h), want[V // 2:])
+    with bcg.Context(0, 3, dims=(4, 2, 2, 3)) as ctx:
+        ctx.set_links_random(5, 0.5)
+        U4 = ora.counter_uniform(5, 0, 0, 2 * ctx.V * 36).view(np.complex128).reshape(ctx.V, 4, 3, 3)
+        Bn = ora.counter_uniform(6, 1, 0, 2 * ctx.V * 9).view(np.complex128).reshape(ctx.V, 3, 3)
+        hb, hx = ctx.field(), ctx.field()
+        ctx.field_random(hb, 6)
+        assert np.array_equal(ctx.download(hb), Bn)
+        ctx.op(hx, hb)
+        oracle.set_lattice((4, 2, 2, 3))
+        try:
+            assert rel(ctx.download(hx), oracle.op(U4, Bn, 0.5, 0.0)) < 1e-13
+        finally:
+            oracle.set_lattice(None)
+
+
 def test_error_paths_4d_and_peer_api(bcg):
     with bcg.Context(0, 3, dims=(4, 2, 2, 2)) as ctx:
         assert ctx.V == 32

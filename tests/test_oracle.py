@@ -134,3 +134,26 @@ def test_4d_extension_properties(oracle):
         assert np.abs(D4x - oracle.D(U1, x)).max() < 1e-14
     finally:
         oracle.set_lattice(None)
+
+
+def test_counter_uniform_generator():
+    """Restatement of the device input generator: range, moments, independence of the split."""
+    import oracle.pyoracle as ora
+    a = ora.counter_uniform(7, 1, 0, 200000)
+    assert a.min() >= -1.0 and a.max() < 1.0
+    assert abs(a.mean()) < 5e-3 and abs(a.var() - 1.0 / 3.0) < 5e-3
+    assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 1e-2
+    # a slab is a slice of the global array; streams and seeds differ
+    assert np.array_equal(ora.counter_uniform(7, 1, 1234, 100), a[1234:1334])
+    assert not np.array_equal(ora.counter_uniform(7, 0, 0, 100), a[:100])
+    assert not np.array_equal(ora.counter_uniform(8, 1, 0, 100), a[:100])
+    assert np.all(a * 2.0 ** 52 == np.round(a * 2.0 ** 52))  # multiples of 2^-52: exact on any machine
+    # SplitMix64 known answer: seed 0, first output of the published generator is 0xE220A8397B1DCDAF
+    z = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    assert int(z) == 0xE220A8397B1DCDAF
+    assert ora.counter_uniform(0, 0, 0, 1)[0] == float(int(z) >> 11) * 2.0 ** -52 - 1.0
+
