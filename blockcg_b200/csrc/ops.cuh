@@ -247,12 +247,22 @@ struct Ops {
                           long long x_begin, long long x_end, double m2, double sigma, int second, const Ctrl* ctrl,
                           int* launches) {
     if (x_end <= x_begin) return 0;
-    const long long items = (x_end - x_begin) * (N / R);
-    const unsigned grid = static_cast<unsigned>((items + 127) / 128);
-    if (second)
-      dirac4_kernel<N, R, true><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
-    else
-      dirac4_kernel<N, R, false><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
+    // right-hand sides per thread: 1 keeps a warp's 16-byte loads within 12 lines per instruction
+    // (3 would spread them over 36); BCG_DIRAC4_R=3 selects the wider variant for comparison
+    static const bool wide = [] { const char* e = std::getenv("BCG_DIRAC4_R"); return e && std::atoi(e) == R && R > 1; }();
+    if (wide) {
+      const unsigned grid = static_cast<unsigned>(((x_end - x_begin) * (N / R) + 127) / 128);
+      if (second)
+        dirac4_kernel<N, R, true><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
+      else
+        dirac4_kernel<N, R, false><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
+    } else {
+      const unsigned grid = static_cast<unsigned>(((x_end - x_begin) * N + 127) / 128);
+      if (second)
+        dirac4_kernel<N, 1, true><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
+      else
+        dirac4_kernel<N, 1, false><<<grid, 128, 0, st>>>(in, p0, out, U, *lat, x_begin, x_end, m2, sigma, ctrl);
+    }
     if (launches) ++*launches;
     return err();
   }
