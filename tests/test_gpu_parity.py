@@ -258,6 +258,27 @@ def test_full_size_properties(bcg, oracle):
             assert rel(ctx.download(xs[s]), Xo[s]) < 1e-10
 
 
+def test_true_residual_floor_long_solve(bcg, oracle):
+    """Thousands of iterations (8^4 sites, m = 1e-3, N = 12): the recurrence residual and the true
+    residual must not drift apart.  The reference's acceptance rule (test/solvers.cpp:116,
+    |B - A X| / |B| < 2 eps) at a harder configuration than its own; the unmodified reference
+    reaches 1.6e-10 here (profiles/r01_parity_full_solve_8x4.json).  Regression test for the
+    update order of X += P M (product first, one addition): accumulating the N terms straight
+    into X left the true residual at 7.7e-10."""
+    V, N, mass, eps = 4096, 12, 1e-3, 1e-10
+    U, B = oracle.make_inputs(V, N, 1)
+    with bcg.Context(V, N, max_shifts=2) as ctx:
+        ctx.set_links(U, mass)
+        hb, hx, hy = ctx.field(B), ctx.field(), ctx.field()
+        info = ctx.solve_sbcgrq_dev([hx, hy], hb, [0.0, 1e-6], eps, 1e-15)
+        assert 2000 < info.iterations < 3400 and info.residual < eps
+        for h, sig in ((hx, 0.0), (hy, 1e-6)):
+            true_res = oracle.true_residual(U, B, ctx.download(h), mass, sig).max()
+            # 1.6e-10 measured, as the reference; 3 eps leaves room for another reduction order
+            assert true_res < 3 * eps, true_res
+            assert abs(ctx.true_residual(h, hb, sig).max() - true_res) < 1e-12
+
+
 def test_inputs_generated_on_device(bcg, oracle):
     """bcg_field_random / bcg_set_links_random against the numpy restatement, bit for bit; a slab
     is a slice of the global array; a solve on generated inputs meets the reference's residual rule."""
