@@ -130,6 +130,7 @@ struct bcg_ctx {
   Ctrl* ctrl_host = nullptr;  // pinned, 2 slots
   cd* mat_host = nullptr;     // pinned staging for N*N matrices (4 slots)
   int work_T = -1, work_Q = -1;
+  int work_Qp = -1;   // Q of the previous iteration (paired multishift update)
   std::vector<int> work_P;
   std::vector<int> host_X;  // handles used by the host-buffer entry points
   int host_B = -1;
@@ -401,6 +402,10 @@ int ensure_work(bcg_ctx* c, int n_shifts) {
   }
   if (c->work_Q < 0) {
     int r = field_alloc(c, &c->work_Q);
+    if (r) return r;
+  }
+  if (c->work_Qp < 0 && n_shifts > 1 && c->ops->shift_update_pair) {
+    int r = field_alloc(c, &c->work_Qp);
     if (r) return r;
   }
   while (static_cast<int>(c->work_P.size()) < n_shifts) {
@@ -831,9 +836,16 @@ int bcg_true_residual(bcg_ctx* c, int x, int b, double sigma, double* res_host) 
 // ---- the iteration loops ---------------------------------------------------------------------
 namespace {
 
+// Shifted systems served every second iteration (shift_pair.cuh).  BCG_PAIR=0 / 1 overrides.
+bool pair_default() {  // read per solve, so that a test can compare both paths in one process
+  const char* e = std::getenv("BCG_PAIR");
+  return e ? std::atoi(e) != 0 : false;
+}
+
 struct LoopPlan {
   int kind;  // 0 BCG, 1 (S)BCGrQ
   int n_shifts;
+  bool pair;  // multishift loop with the paired update
   cd* P0;
   cd* T;
   cd* Q;  // BCG: R
@@ -875,8 +887,13 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
                                                                       gw1);
   ++*launches;
   CU(cudaGetLastError());
-  KL(c->ops->shift_update(c->stream, p.Q, &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
-                          p.kind == 1 ? 1 : 0, p.kind == 1 ? 0 : 1, c->ctrl, c->sms, launches));
+  if (p.pair)
+    KL(c->ops->shift_update_pair(c->stream, p.Q, fptr(c, c->work_Qp), &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1),
+                                 c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0), c->mats + c->L.B(0, 0), c->V, c->ctrl,
+                                 c->sms, launches));
+  else
+    KL(c->ops->shift_update(c->stream, p.Q, &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
+                            p.kind == 1 ? 1 : 0, p.kind == 1 ? 0 : 1, c->ctrl, c->sms, launches));
   return halo_refresh(c, p.P0, 3 * c->N, c->ctrl, launches);
 }
 
@@ -892,6 +909,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
   const void* sigbits;
   std::memcpy(&sigbits, &sig, sizeof sigbits);
   key.push_back(sigbits);
+  key.push_back(p.pair ? &c->work_Qp : nullptr);
   GraphCache& g = c->graph;
   if (!g.exec || g.kind != p.kind || g.n_shifts != p.n_shifts || g.batch != batch || g.key != key) {
     if (g.exec) {
@@ -996,6 +1014,8 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   if (r) return r;
   r = init_ctrl(c, n_shifts, sigma, eps, eps_shifts, max_it);
   if (r) return r;
+  const bool pair = pair_default() && n_shifts > 1 && c->ops->shift_update_pair != nullptr && c->work_Qp >= 0;
+  c->L.pair = pair ? 1 : 0;
   int64_t launches = 0;
   int l = 0;
   CU(cudaEventRecord(c->ev[0], c->stream));
@@ -1017,6 +1037,7 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   LoopPlan p;
   std::memset(&p, 0, sizeof p);
   p.kind = 1;
+  p.pair = pair;
   p.n_shifts = n_shifts;
   p.T = fptr(c, c->work_T);
   p.Q = Q;
@@ -1055,6 +1076,7 @@ int solve_bcg(bcg_ctx* c, int x, int b, double eps, int max_it, bcg_solve_info* 
   CU(cudaSetDevice(c->device));
   int r = ensure_work(c, 1);
   if (r) return r;
+  c->L.pair = 0;
   r = init_ctrl(c, 1, nullptr, eps, 0.0, max_it);
   if (r) return r;
   int64_t launches = 0;

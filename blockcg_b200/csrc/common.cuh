@@ -86,6 +86,7 @@ struct Ctrl {
   int conv[kMaxShifts];            // shift converged in the current iteration
   double resid_shift[kMaxShifts];  // last shifted residual estimate
   double sigma[kMaxShifts];
+  int n_act[2];                    // n_unconv of the last odd / even iteration ([iter & 1]; paired multishift update)
 };
 
 // ---- peer-memory exchange between the ranks of a slab decomposition (NVLink P2P) -------------

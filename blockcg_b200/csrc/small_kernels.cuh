@@ -37,7 +37,12 @@ struct MatLayout {
   __host__ __device__ size_t B(int s) const { return (M_FIXED_COUNT + S + s) * nn(); }
   __host__ __device__ size_t alpha_s(int s) const { return (M_FIXED_COUNT + 2 * S + s) * nn(); }
   __host__ __device__ size_t beta_s(int s) const { return (M_FIXED_COUNT + 3 * S + s) * nn(); }
-  __host__ __device__ size_t total() const { return (M_FIXED_COUNT + 4 * S) * nn(); }
+  // paired multishift update (shift_pair.cuh): the operands of odd iterations live in a second set of
+  // slots, so that the even iteration's launch still finds them
+  int pair = 0;
+  __host__ __device__ size_t A(int s, int iter) const { return ((pair && (iter & 1)) ? M_FIXED_COUNT + 4 * S + s : M_FIXED_COUNT + s) * nn(); }
+  __host__ __device__ size_t B(int s, int iter) const { return ((pair && (iter & 1)) ? M_FIXED_COUNT + 5 * S + s : M_FIXED_COUNT + S + s) * nn(); }
+  __host__ __device__ size_t total() const { return (M_FIXED_COUNT + 6 * S) * nn(); }
 };
 
 // (row, column) of every linear matrix index, filled once per kernel: an integer division by
@@ -637,7 +642,7 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
       ainv_g[e] = Ainv[e];
       mats[L.fixed(M_ALPHA) + e] = alpha[e];
       mats[L.fixed(M_NEGALPHA) + e] = cmake(-alpha[e].x, -alpha[e].y);
-      mats[L.A(0) + g_il[e]] = ad[e];
+      mats[L.A(0, iter) + g_il[e]] = ad[e];
     }
     return;
   }
@@ -713,7 +718,7 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
       rho_g[e] = rho[e];
       mats[L.fixed(M_RHO_CUR) + e] = (i == j) ? cmake(__drcp_rn(rho[e].x), 0.0) : rho[e];  // diagonal of chol: real > 0
       mats[L.fixed(M_DELTA) + e] = dn[e];
-      mats[L.B(0) + g_il[e]] = cconj(rho[j + N * i]);
+      mats[L.B(0, iter) + g_il[e]] = cconj(rho[j + N * i]);
     }
     if (threadIdx.x == 0) {
       double r = 0.0;
@@ -728,6 +733,7 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
       // the copies the next A-step reads (its CTAs must not race with CTA 0's own updates)
       ctrl->iter_b = iter;
       ctrl->n_unconv_b = ctrl->n_unconv;
+      ctrl->n_act[iter & 1] = ctrl->n_unconv;
       // while (residual > eps && iter < max_iterations)  -- NaN ends the loop as in the reference
       if (!(r > ctrl->eps) || iter >= ctrl->max_it) ctrl->stop = 1;
       if (info >= 0) {
@@ -770,8 +776,8 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   sm_mm_adj(t1, beta, rho, N);  // B_s = beta_s rho^dag
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     mats[L.alpha_s(sh) + e] = t2[e];
-    mats[L.A(sh) + g_il[e]] = t2[e];
-    mats[L.B(sh) + g_il[e]] = t1[e];
+    mats[L.A(sh, iter) + g_il[e]] = t2[e];
+    mats[L.B(sh, iter) + g_il[e]] = t1[e];
   }
   if (threadIdx.x == 0) {
     double r = 0.0;
