@@ -131,6 +131,7 @@ struct bcg_ctx {
   cd* mat_host = nullptr;     // pinned staging for N*N matrices (4 slots)
   int work_T = -1, work_Q = -1;
   int work_Qp = -1;   // Q of the previous iteration (paired multishift update)
+  Ctrl* bench_ctrl = nullptr;  // micro-benchmark of the paired update: control blocks of an odd and an even iteration
   std::vector<int> work_P;
   std::vector<int> host_X;  // handles used by the host-buffer entry points
   int host_B = -1;
@@ -542,6 +543,7 @@ int bcg_ctx_destroy(bcg_ctx* c) {
   cudaFree(c->mats);
   cudaFree(c->b_norm);
   cudaFree(c->ctrl);
+  cudaFree(c->bench_ctrl);
   if (c->ctrl_host) cudaFreeHost(c->ctrl_host);
   if (c->mat_host) cudaFreeHost(c->mat_host);
   for (auto& e : c->ev)
@@ -839,7 +841,7 @@ namespace {
 // Shifted systems served every second iteration (shift_pair.cuh).  BCG_PAIR=0 / 1 overrides.
 bool pair_default() {  // read per solve, so that a test can compare both paths in one process
   const char* e = std::getenv("BCG_PAIR");
-  return e ? std::atoi(e) != 0 : false;
+  return e ? std::atoi(e) != 0 : true;
 }
 
 struct LoopPlan {
@@ -1199,7 +1201,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   const double m2 = c->mass * c->mass;
   ShiftPtrs fp;
   std::memset(&fp, 0, sizeof fp);
-  if (which == 4 || which == 7 || which == 8) {
+  if (which == 4 || which == 7 || which == 8 || which == 13) {
     if (nh < 1 + 2 * n_shifts || n_shifts < 1 || n_shifts > c->S) return fail(c, BCG_ERR_INVALID, "need 1+2S handles");
     for (int s = 0; s < n_shifts; ++s) {
       fp.X[s] = fptr(c, h[1 + 2 * s]);
@@ -1208,8 +1210,33 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   } else if (nh < 2) {
     return fail(c, BCG_ERR_INVALID, "need 2 handles");
   }
+  MatLayout Lp = c->L;
+  Lp.pair = 1;
+  if (which == 13) {  // paired multishift update: one repetition = an odd and an even iteration's launch
+    if (!c->ops->shift_update_pair) return fail(c, BCG_ERR_INVALID, "no paired multishift kernel at N=%d", c->N);
+    if (c->work_Qp < 0) {
+      int r_ = field_alloc(c, &c->work_Qp);
+      if (r_) return r_;
+    }
+    if (!c->bench_ctrl) CU(cudaMalloc(&c->bench_ctrl, 2 * sizeof(Ctrl)));
+    Ctrl hc[2];
+    std::memset(hc, 0, sizeof hc);
+    for (int i = 0; i < 2; ++i) {
+      hc[i].iter = 1 + i;
+      hc[i].n_unconv = n_shifts;
+      hc[i].n_shifts = n_shifts;
+      hc[i].n_act[1] = n_shifts;
+    }
+    CU(cudaMemcpy(c->bench_ctrl, hc, sizeof hc, cudaMemcpyHostToDevice));
+  }
   auto body = [&](int* l) -> int {
     switch (which) {
+      case 13:
+        for (int i = 0; i < 2; ++i)
+          KL(c->ops->shift_update_pair(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
+                                       c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
+                                       c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l));
+        break;
       case 0: {
         int np_ = 0;
         int r_ = apply_op(c, fptr(c, h[0]), fptr(c, h[1]), 0.0, true, nullptr, l, nullptr, &np_);
@@ -1274,10 +1301,12 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
     std::vector<cd> I(nn, make_double2(0, 0)), Z(nn, make_double2(0, 0));
     for (int i = 0; i < c->N; ++i) I[i + c->N * i] = make_double2(1.0, 0.0);
     for (size_t e = 0; e < nn; ++e) Z[e] = make_double2(1e-3 * ((e * 7) % 5), -1e-3 * ((e * 3) % 7));
-    CU(cudaMemcpy(mat(c, M_SCRATCH), (which == 4 || which == 7 || which == 8) ? I.data() : Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(mat(c, M_SCRATCH), (which == 4 || which == 7 || which == 8 || which == 13) ? I.data() : Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
     for (int s = 0; s < c->S; ++s) {
       CU(cudaMemcpy(c->mats + c->L.A(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(c->mats + c->L.B(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(c->mats + Lp.A(s, 1), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(c->mats + Lp.B(s, 1), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
     }
   }
   int dummy = 0;

@@ -13,7 +13,8 @@
 // (14 + 4 (S-1) + 1) F bytes instead of 2 (4 S + 2) F (46 F against 76 F at S = 9), with the
 // arithmetic, its order and hence every bit of the result unchanged.  A shift that retired
 // between the two iterations gets the first update only; if the loop ends on a "first"
-// iteration (`stop` is set by its B-step) that launch does the plain update of every system.
+// iteration (`stop` is set by its B-step), or once only the unshifted system is left, the launch
+// does the plain update.
 // The phase is read from the device-side iteration counter, so every launch of a captured
 // graph is the same node.
 //
@@ -82,12 +83,17 @@ shift_pair_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
   const bool odd = (iter & 1) != 0;
   PairPlan plan;
   plan.n2 = ctrl->n_unconv;
-  if (odd) {
-    plan.mode = ctrl->stop ? 0 : 1;
-    plan.n_items = ctrl->stop ? 1 + plan.n2 : 2;
-  } else {
+  // nothing is deferred when the loop ends on this iteration or no shifted system is active any more
+  const int n1 = odd ? plan.n2 : ctrl->n_act[1];  // systems active in the odd iteration of this pair
+  if (odd && !ctrl->stop && n1 > 1) {
+    plan.mode = 1;
+    plan.n_items = 2;
+  } else if (!odd && n1 > 1) {
     plan.mode = 2;
-    plan.n_items = 2 + ctrl->n_act[1];  // systems that were active in the odd iteration before
+    plan.n_items = 2 + n1;
+  } else {
+    plan.mode = 0;
+    plan.n_items = 1 + plan.n2;
   }
   const cd* Acur = odd ? Aodd : Aeven;
   const cd* Bcur = odd ? Bodd : Beven;

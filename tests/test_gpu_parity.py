@@ -279,11 +279,13 @@ def test_true_residual_floor_long_solve(bcg, oracle):
             assert abs(ctx.true_residual(h, hb, sig).max() - true_res) < 1e-12
 
 
-@pytest.mark.parametrize("V,N,max_it", [(1000, 12, 10 ** 6), (1000, 12, 37), (777, 4, 10 ** 6), (130, 8, 52), (64, 3, 10 ** 6)])
-def test_paired_multishift_update_is_bit_identical(bcg, oracle, V, N, max_it, monkeypatch):
+@pytest.mark.parametrize("V,N,max_it,eps_shifts", [(1000, 12, 10 ** 6, 1e-9), (1000, 12, 37, 1e-9),
+                                                   (777, 4, 10 ** 6, 1e-5), (130, 8, 52, 1e-9), (64, 3, 10 ** 6, 1e-9)])
+def test_paired_multishift_update_is_bit_identical(bcg, oracle, V, N, max_it, eps_shifts, monkeypatch):
     """Shifted systems served every second iteration (shift_pair.cuh) against the plain loop: the
     same arithmetic in the same order, so every bit of every solution must agree -- full solves
-    (shifts retire on the way), solves cut at an odd and at an even iteration count."""
+    (shifts retire on the way; with eps_shifts = 1e-5 all of them do and the loop falls back to the
+    plain update), solves cut at an odd and at an even iteration count."""
     mass, eps = 0.02, 1e-10
     shifts = [0.0, 1e-4, 1e-2, 0.1, 0.5, 0.9]
     U, B = oracle.make_inputs(V, N, 5)
@@ -294,11 +296,13 @@ def test_paired_multishift_update_is_bit_identical(bcg, oracle, V, N, max_it, mo
             ctx.set_links(U, mass)
             hb = ctx.field(B)
             xs = [ctx.field() for _ in shifts]
-            info = ctx.solve_sbcgrq_dev(xs, hb, shifts, eps, 1e-9, max_it)
+            info = ctx.solve_sbcgrq_dev(xs, hb, shifts, eps, eps_shifts, max_it)
             out[mode] = (info.iterations, info.n_unconverged, [ctx.download(h) for h in xs])
     assert out["0"][0] == out["1"][0] and out["0"][1] == out["1"][1]
     if max_it > 1000:
         assert out["0"][1] < len(shifts)  # some shifted systems did retire before the end
+    if eps_shifts > 1e-6:
+        assert out["0"][1] == 1
     for a, b in zip(out["0"][2], out["1"][2]):
         assert np.array_equal(a, b)
 
