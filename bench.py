@@ -301,14 +301,17 @@ def run_ours(args, w, wname):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(wname, {}) if world == 1 else {}
     except Exception:
         pass
-    # The loop serves the shifted systems every second iteration (shift_pair.cuh): an odd launch moves
-    # 7 F (Q in/out, Q kept, P_0, X_0), the even one (7 + 4 (S-1)) F; "shift_pair" is the AVERAGE launch of
-    # such a pair.  "shift_update" (the plain kernel, every system every iteration) is timed for comparison.
+    # The loop serves the shifted systems every second iteration (shift_pair.cuh).  "shift_pair" is the
+    # AVERAGE launch of an odd + even pair.  Its numerator is the fixed per-unit figure of SURVEY 8(d) x the
+    # units a pair processes -- 2 back-substitutions (2 F each) and 2 S system updates (4 F each), i.e.
+    # (2 + 4 S) F per launch, the same figure as for the plain kernel -- so that serving X_s, P_s once per two
+    # iterations shows up as bandwidth; the bytes the pair really moves ((14 + 4 (S-1)) F / 2 per launch) are
+    # the ncu figure in `traffic`.  "shift_update" (plain kernel, every system every iteration): for comparison.
     paired = S > 1 and os.environ.get("BCG_PAIR", "1") != "0"
     todo = [("dirac_gram", 0, 2, 1, 2 * F + Ub, 1), ("dirac", 1, 2, 1, 2 * F + Ub, 1), ("axpy_gram", 3, 2, 1, 3 * F, 1),
             ("shift_update", 4, 1 + 2 * S, S, (2 + 4 * S) * F, 1)]
     if paired:
-        todo.append(("shift_pair", 13, 1 + 2 * S, S, (14 + 4 * (S - 1)) * F / 2, 2))
+        todo.append(("shift_pair", 13, 1 + 2 * S, S, (2 + 4 * S) * F, 2))
     for name, which, nh, ns, nbytes, per_rep in todo:
         ms, _ = ctx.bench_kernel(which, 20 // per_rep, hs[:nh], ns)
         ms /= per_rep
@@ -324,6 +327,14 @@ def run_ours(args, w, wname):
                 "frac": kern[dom]["frac"], "traffic": kern[dom]["traffic"], "peak_source": peak_src,
                 "share_of_iteration": kern[dom]["ms"] / it_ms,
                 "alg_bytes_per_launch": kern[dom]["alg_bytes"], "ms_per_launch": kern[dom]["ms"]}
+    if dom == "shift_pair":
+        moved = (14 + 4 * (S - 1)) * F / 2
+        roofline["note"] = ("average launch of an odd+even pair; numerator = fixed per-unit bytes (2 F per back-substitution, "
+                            "4 F per system update) x units; the pair touches X_s, P_s once per two iterations, so it moves "
+                            "%.3g B per launch (%.0f GB/s = %.2f of peak) and is limited on chip: ncu of the even launch "
+                            "L1/shared 78 %%, FP64 57 %%, DRAM 45 %%" % (moved, moved / kern[dom]["ms"] / 1e6,
+                                                                      moved / kern[dom]["ms"] / 1e6 / peak))
+        roofline["moved_bytes_per_launch"] = moved
     dirac = kern["dirac_gram"]
 
     if rank != 0:

@@ -63,7 +63,7 @@ def run(V, N, S, reps, seed=0):
             ("shift_direct_S%d" % S, 7, hs[:1 + 2 * S], S, (2 + 4 * S) * F),
         ]
         if S > 1:  # paired update: one repetition = odd + even launch, "ms" is the pair
-            kernels.append(("shift_pair_S%d" % S, 13, hs[:1 + 2 * S], S, (14 + 4 * (S - 1)) * F))
+            kernels.append(("shift_pair_S%d" % S, 13, hs[:1 + 2 * S], S, 2 * (2 + 4 * S) * F))  # fixed per-unit bytes
         for name, which, handles, ns, bytes_alg in kernels:
             ms, nl = ctx.bench_kernel(which, reps, handles, ns)
             out[name] = {"ms": ms, "alg_GBps": bytes_alg / ms / 1e6, "launches": nl}
