@@ -81,3 +81,17 @@ def test_host_mirror_compiles(lib):
     subprocess.run(["make", "-C", host, "-B", "all"], check=True, capture_output=True)
     assert os.path.exists(os.path.join(host, "test_solvers"))
     assert os.path.exists(os.path.join(host, "benchmark"))
+
+
+def test_makefile_tracks_every_header():
+    """Every header of the CUDA sources is a prerequisite of the objects: a header left out once kept a
+    stale kernel in the library although `make` reported it up to date."""
+    import glob
+    import re
+    csrc = os.path.join(ROOT, "blockcg_b200", "csrc")
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    hdrs = re.search(r"^HDRS\s*=\s*(.*)$", mk, re.M).group(1).split()
+    have = {os.path.basename(h) for h in hdrs}
+    want = {os.path.basename(f) for f in glob.glob(os.path.join(csrc, "*.cuh")) + glob.glob(os.path.join(csrc, "*.h"))}
+    assert want <= have, sorted(want - have)
+
