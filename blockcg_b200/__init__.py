@@ -8,4 +8,4 @@ Only what the path needs lives here:
   solvers.py  the reference's call signatures for Python callers
 """
 from .capi import BcgError, Context, SolveInfo, load  # noqa: F401
-from .solvers import BCG, BCGrQ, SBCGrQ, block_fermion_field, dirac_op  # noqa: F401
+from .solvers import BCG, BCGrQ, CG, SBCGrQ, SCG, block_fermion_field, dirac_op  # noqa: F401

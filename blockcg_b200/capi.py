@@ -29,7 +29,8 @@ EXPORTS = [
     "bcg_field_upload", "bcg_field_download", "bcg_field_random", "bcg_set_links_random", "bcg_field_zero", "bcg_field_copy", "bcg_op", "bcg_gram",
     "bcg_add", "bcg_add_scalar", "bcg_rescale_add", "bcg_trsm", "bcg_thinqr", "bcg_true_residual",
     "bcg_solve_bcg_dev", "bcg_solve_bcgrq_dev", "bcg_solve_sbcgrq_dev", "bcg_solve_bcg", "bcg_solve_bcgrq",
-    "bcg_solve_sbcgrq", "bcg_bench_kernel",
+    "bcg_solve_sbcgrq", "bcg_bench_kernel", "bcg_solve_cg_dev", "bcg_solve_scg_dev", "bcg_solve_cg", "bcg_solve_scg",
+    "bcg_last_solve_stats", "bcg_small_inverse", "bcg_small_lu_solve", "bcg_set_loop_profile", "bcg_get_loop_profile",
 ]
 
 
@@ -39,6 +40,12 @@ class SolveInfo(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("n_shifts", C.c_int), ("paired", C.c_int),
+                ("active_hist", C.c_uint32 * (MAX_SHIFTS + 1)), ("shift_update_field_passes", C.c_uint64),
+                ("resid_shift", C.c_double * MAX_SHIFTS)]
 
 
 class BcgError(RuntimeError):
@@ -100,6 +107,17 @@ def load():
     lib.bcg_solve_bcgrq.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.POINTER(SolveInfo)]
     lib.bcg_solve_sbcgrq.argtypes = [C.c_void_p, C.POINTER(_dp), _dp, _dp, C.c_int, C.c_double, C.c_double,
                                      C.c_int, C.POINTER(SolveInfo)]
+    lib.bcg_solve_cg_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(SolveInfo)]
+    lib.bcg_solve_scg_dev.argtypes = [C.c_void_p, _ip, C.c_int, _dp, C.c_int, C.c_double, C.c_double, C.c_int,
+                                      C.POINTER(SolveInfo)]
+    lib.bcg_solve_cg.argtypes = [C.c_void_p, _dp, _dp, C.c_double, C.c_int, C.POINTER(SolveInfo)]
+    lib.bcg_solve_scg.argtypes = [C.c_void_p, C.POINTER(_dp), _dp, _dp, C.c_int, C.c_double, C.c_double,
+                                  C.c_int, C.POINTER(SolveInfo)]
+    lib.bcg_last_solve_stats.argtypes = [C.c_void_p, C.POINTER(SolveStats)]
+    lib.bcg_set_loop_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.bcg_get_loop_profile.argtypes = [C.c_void_p, _dp, _ip]
+    lib.bcg_small_inverse.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _ip]
+    lib.bcg_small_lu_solve.argtypes = [C.c_void_p, _dp, _dp, _dp]
     lib.bcg_bench_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp,
                                      C.POINTER(C.c_int64)]
     _lib = lib
@@ -306,6 +324,52 @@ class Context:
         self._ck(self.lib.bcg_solve_sbcgrq(self._h, ptrs, _dptr(B), _dptr(sig), len(Xs), eps, eps_shifts,
                                            int(max_iterations), C.byref(info)))
         return info
+
+    # ---- CG / SCG (one right-hand side, src/standard_solvers.cpp) ----
+    def solve_cg(self, X, B, eps=1e-15, max_iterations=1000000):
+        info = SolveInfo()
+        self._ck(self.lib.bcg_solve_cg(self._h, _dptr(X), _dptr(B), eps, int(max_iterations), C.byref(info)))
+        return info
+
+    def solve_scg(self, Xs, B, sigma, eps=1e-15, eps_shifts=1e-15, max_iterations=1000000):
+        info = SolveInfo()
+        ptrs = (_dp * len(Xs))(*[_dptr(x) for x in Xs])
+        sig = np.ascontiguousarray(sigma, dtype=np.float64)
+        self._ck(self.lib.bcg_solve_scg(self._h, ptrs, _dptr(B), _dptr(sig), len(Xs), eps, eps_shifts,
+                                        int(max_iterations), C.byref(info)))
+        return info
+
+    def last_solve_stats(self):
+        """Active-system histogram, bytes moved by the multishift update and per-system residual
+        estimates of the last solve on this context."""
+        st = SolveStats()
+        self._ck(self.lib.bcg_last_solve_stats(self._h, C.byref(st)))
+        return {"iterations": st.iterations, "n_shifts": st.n_shifts, "paired": bool(st.paired),
+                "active_hist": list(st.active_hist), "shift_update_field_passes": int(st.shift_update_field_passes),
+                "resid_shift": list(st.resid_shift)[:max(st.n_shifts, 1)]}
+
+    def set_loop_profile(self, n_iterations):
+        """Time the first n_iterations of the next solve stage by stage (CUDA events inside the loop)."""
+        self._ck(self.lib.bcg_set_loop_profile(self._h, int(n_iterations)))
+
+    def loop_profile(self):
+        ms = (C.c_double * 8)()
+        n = C.c_int(0)
+        self._ck(self.lib.bcg_get_loop_profile(self._h, ms, C.byref(n)))
+        keys = ["dirac_gram", "step_a", "axpy_gram", "step_b", "shift_odd", "shift_even", "halo", "iteration"]
+        return {"iterations": n.value, "ms": dict(zip(keys, [float(v) for v in ms]))}
+
+    # ---- the device N x N routines in isolation (unit tests) ----
+    def small_inverse(self, A, pivot=True):
+        out = np.empty((self.N, self.N), np.complex128)
+        info = C.c_int(0)
+        self._ck(self.lib.bcg_small_inverse(self._h, _dptr(mat_to_cm(A)), _dptr(out), 1 if pivot else 0, C.byref(info)))
+        return mat_from_cm(out, self.N), info.value
+
+    def small_lu_solve(self, A, B):
+        out = np.empty((self.N, self.N), np.complex128)
+        self._ck(self.lib.bcg_small_lu_solve(self._h, _dptr(mat_to_cm(A)), _dptr(mat_to_cm(B)), _dptr(out)))
+        return mat_from_cm(out, self.N)
 
     def bench_kernel(self, which, reps, handles, n_shifts=1):
         ms = C.c_double(0)

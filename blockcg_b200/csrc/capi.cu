@@ -95,7 +95,7 @@ using namespace bcg;
 
 struct GraphCache {
   cudaGraphExec_t exec = nullptr;
-  int kind = -1;  // 0 BCG, 1 (S)BCGrQ
+  int kind = -1;  // 0 BCG, 1 (S)BCGrQ, 2 CG / SCG
   int n_shifts = 0;
   int batch = 0;
   int launches = 0;
@@ -145,6 +145,11 @@ struct bcg_ctx {
   bool p2p_ready = false;
   unsigned epoch = 0;  // solves started on this context (sequence-number base of the exchange)
   GraphCache graph;
+  // in-loop profile (bcg_set_loop_profile): the first `prof_want` iterations of the next solve are enqueued
+  // kernel by kernel with an event after each, instead of as a graph batch
+  int prof_want = 0, prof_n = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::string err;
   size_t small_smem = 0;
 };
@@ -531,6 +536,7 @@ int bcg_ctx_destroy(bcg_ctx* c) {
     cudaStreamSynchronize(c->stream);
   }
   if (c->graph.exec) cudaGraphExecDestroy(c->graph.exec);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   if (c->comm) ncclCommDestroy(c->comm);
   for (int r = 0; r < c->nranks && r < kMaxRanks; ++r)
     if (c->p2p_peer[r] && c->p2p_peer[r] != c->p2p_local) cudaIpcCloseMemHandle(c->p2p_peer[r]);
@@ -681,6 +687,7 @@ int bcg_field_alloc(bcg_ctx* c, int* h) {
 }
 int bcg_field_free(bcg_ctx* c, int h) {
   if (!c || !valid(c, h)) return fail(c, BCG_ERR_INVALID, "bad field handle %d", h);
+  CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaFree(c->fields[h]));
   c->fields[h] = nullptr;
@@ -688,6 +695,7 @@ int bcg_field_free(bcg_ctx* c, int h) {
 }
 int bcg_field_upload(bcg_ctx* c, int h, const double* host) {
   if (!c || !valid(c, h) || !host) return fail(c, BCG_ERR_INVALID, "bad argument to field_upload");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(fptr(c, h), host, static_cast<size_t>(c->V) * site_elems(c) * sizeof(cd),
                      cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -695,6 +703,7 @@ int bcg_field_upload(bcg_ctx* c, int h, const double* host) {
 }
 int bcg_field_download(bcg_ctx* c, int h, double* host) {
   if (!c || !valid(c, h) || !host) return fail(c, BCG_ERR_INVALID, "bad argument to field_download");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(host, fptr(c, h), static_cast<size_t>(c->V) * site_elems(c) * sizeof(cd),
                      cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -702,11 +711,13 @@ int bcg_field_download(bcg_ctx* c, int h, double* host) {
 }
 int bcg_field_zero(bcg_ctx* c, int h) {
   if (!c || !valid(c, h)) return fail(c, BCG_ERR_INVALID, "bad field handle %d", h);
+  CU(cudaSetDevice(c->device));
   CU(cudaMemsetAsync(c->fields[h], 0, field_elems(c) * sizeof(cd), c->stream));
   return BCG_OK;
 }
 int bcg_field_copy(bcg_ctx* c, int dst, int src) {
   if (!c || !valid(c, dst) || !valid(c, src)) return fail(c, BCG_ERR_INVALID, "bad field handle");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(c->fields[dst], c->fields[src], field_elems(c) * sizeof(cd), cudaMemcpyDeviceToDevice,
                      c->stream));
   return BCG_OK;
@@ -726,7 +737,10 @@ int bcg_op(bcg_ctx* c, int out, int in, double sigma, double* gram_host) {
     const size_t nn = c->L.nn();
     gram_reduce_kernel<<<1, kSmallThreads, (1 + kRedSlices) * nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, np, c->N);
     CU(cudaGetLastError());
-    if (c->nranks > 1) NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
+    if (c->nranks > 1) {
+      if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
+      NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
+    }
     CU(cudaMemcpyAsync(gram_host, c->gred, nn * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -845,7 +859,7 @@ bool pair_default() {  // read per solve, so that a test can compare both paths 
 }
 
 struct LoopPlan {
-  int kind;  // 0 BCG, 1 (S)BCGrQ
+  int kind;  // 0 BCG, 1 (S)BCGrQ, 2 CG / SCG (scalar coefficients, N_rhs = 1)
   int n_shifts;
   bool pair;  // multishift loop with the paired update
   cd* P0;
@@ -856,7 +870,11 @@ struct LoopPlan {
 };
 
 // enqueue one iteration on c->stream
-int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
+// marks (optional): 7 events, recorded before the stencil and after each of the six stages
+// (stencil+Gram, A-step, Q update+Gram, B-step, multishift update, halo)
+int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t* marks = nullptr) {
+#define BCG_MARK(i) do { if (marks) CU(cudaEventRecord(marks[i], c->stream)); } while (0)
+  BCG_MARK(0);
   const cd* gsrc;
   int nsrc;
   // slab decomposition with mapped peer buffers: the Gram kernels push their block to every
@@ -870,17 +888,54 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
   if (r) return r;
   r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
+  if (p.kind == 2) {
+    // CG / SCG (src/standard_solvers.cpp): alpha = r.r / p.t ; r -= t alpha (+ r.r) ; beta and the
+    // shifted scalars ; one pass over every active system.  Q is the residual r here.
+    BCG_MARK(1);
+    scg_step_a_kernel<<<1, kScalarThreads, 0, c->stream>>>(mat(c, M_NEGALPHA), gsrc, nsrc, c->ctrl);
+    ++*launches;
+    CU(cudaGetLastError());
+    BCG_MARK(2);
+    np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches, nullptr);
+    KL(np);
+    r = gram_finalize(c, np, &gsrc, &nsrc, launches, false);
+    if (r) return r;
+    BCG_MARK(3);
+    scg_step_b_kernel<<<1, kScalarThreads, 0, c->stream>>>(gsrc, nsrc, c->ctrl);
+    ++*launches;
+    CU(cudaGetLastError());
+    BCG_MARK(4);
+    ScalarPtrs sp;
+    std::memset(&sp, 0, sizeof sp);
+    for (int s = 0; s < p.n_shifts; ++s) {
+      sp.X[s] = p.fp.X[s];
+      sp.P[s] = p.fp.P[s];
+    }
+    const long long n = 3 * c->V;
+    const unsigned blocks = static_cast<unsigned>(std::min<long long>((n + 255) / 256, 8LL * c->sms));
+    scg_update_kernel<<<blocks, 256, 0, c->stream>>>(sp, p.Q, n, c->ctrl);
+    ++*launches;
+    CU(cudaGetLastError());
+    BCG_MARK(5);
+    r = halo_refresh(c, p.P0, 3 * c->N, c->ctrl, launches);
+    if (r) return r;
+    BCG_MARK(6);
+    return BCG_OK;
+  }
+  BCG_MARK(1);
   if (p.kind == 1)
     rq_step_a_kernel<<<p.n_shifts, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   else
     bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   ++*launches;
   CU(cudaGetLastError());
+  BCG_MARK(2);
   np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches,
                          fused ? &gp1 : nullptr);
   KL(np);
   r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
+  BCG_MARK(3);
   if (p.kind == 1)
     rq_step_b_kernel<<<p.n_shifts, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc,
                                                                              c->ctrl, gw1);
@@ -889,6 +944,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
                                                                       gw1);
   ++*launches;
   CU(cudaGetLastError());
+  BCG_MARK(4);
   if (p.pair)
     KL(c->ops->shift_update_pair(c->stream, p.Q, fptr(c, c->work_Qp), &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1),
                                  c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0), c->mats + c->L.B(0, 0), c->V, c->ctrl,
@@ -896,7 +952,12 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches) {
   else
     KL(c->ops->shift_update(c->stream, p.Q, &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
                             p.kind == 1 ? 1 : 0, p.kind == 1 ? 0 : 1, c->ctrl, c->sms, launches));
-  return halo_refresh(c, p.P0, 3 * c->N, c->ctrl, launches);
+  BCG_MARK(5);
+  r = halo_refresh(c, p.P0, 3 * c->N, c->ctrl, launches);
+  if (r) return r;
+  BCG_MARK(6);
+  return BCG_OK;
+#undef BCG_MARK
 }
 
 int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launches_total) {
@@ -907,10 +968,14 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     key.push_back(p.fp.X[s]);
     key.push_back(p.fp.P[s]);
   }
-  double sig = p.sigma0;
-  const void* sigbits;
-  std::memcpy(&sigbits, &sig, sizeof sigbits);
-  key.push_back(sigbits);
+  // arguments passed BY VALUE to the captured kernels: the shift sigma_0 and m^2 (set_links may have
+  // changed the mass since the graph was captured; the links themselves are read through a pointer
+  // that never changes), as bit patterns
+  for (double byval : {p.sigma0, c->mass * c->mass}) {
+    const void* bits;
+    std::memcpy(&bits, &byval, sizeof bits);
+    key.push_back(bits);
+  }
   key.push_back(p.pair ? &c->work_Qp : nullptr);
   GraphCache& g = c->graph;
   if (!g.exec || g.kind != p.kind || g.n_shifts != p.n_shifts || g.batch != batch || g.key != key) {
@@ -937,6 +1002,47 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     g.batch = batch;
     g.launches = launches;
     g.key = key;
+  }
+  // optional in-loop profile: the first iterations one kernel at a time with an event after each stage
+  // (same kernels, same stream, same control flow on the device; only the submission differs)
+  c->prof_n = 0;
+  if (c->prof_want > 0) {
+    const int P = c->prof_want;
+    while (static_cast<int>(c->prof_ev.size()) < 7 * P) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      c->prof_ev.push_back(e);
+    }
+    int l = 0;
+    for (int i = 0; i < P; ++i) {
+      int r = enqueue_iteration(c, p, &l, c->prof_ev.data() + 7 * i);
+      if (r) return r;
+    }
+    *launches_total += l;
+    CU(cudaMemcpyAsync(c->ctrl_host, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const int ran = c->ctrl_host[0].iter < P ? c->ctrl_host[0].iter : P;  // a solve shorter than the window
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n_odd = 0, n_even = 0;
+    for (int i = 0; i < ran; ++i) {
+      const cudaEvent_t* ev = c->prof_ev.data() + 7 * i;
+      float ms[6];
+      for (int k = 0; k < 6; ++k) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+      const bool odd = ((i + 1) & 1) != 0;  // iteration number i + 1
+      acc[0] += ms[0];
+      acc[1] += ms[1];
+      acc[2] += ms[2];
+      acc[3] += ms[3];
+      acc[odd ? 4 : 5] += ms[4];
+      acc[6] += ms[5];
+      (odd ? n_odd : n_even) += 1;
+      for (int k = 0; k < 6; ++k) acc[7] += ms[k];
+    }
+    for (int k = 0; k < 8; ++k) c->prof_ms[k] = ran ? acc[k] / ran : 0.0;
+    c->prof_ms[4] = n_odd ? acc[4] / n_odd : 0.0;   // per odd / per even iteration
+    c->prof_ms[5] = n_even ? acc[5] / n_even : 0.0;
+    c->prof_n = ran;
+    c->prof_want = 0;  // one solve
   }
   // pipelined submission: look at batch i-1's mirror after submitting batch i
   int submitted = 0;
@@ -1126,6 +1232,71 @@ int solve_bcg(bcg_ctx* c, int x, int b, double eps, int max_it, bcg_solve_info* 
   return finish_info(c, info, launches);
 }
 
+// CG (n_shifts = 1, sigma = 0, eps_shifts = 0) and SCG on an N_rhs = 1 context
+int solve_scg(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts, double eps, double eps_shifts,
+              int max_it, bcg_solve_info* info) {
+  if (!c) return BCG_ERR_INVALID;
+  if (c->N != 1) return fail(c, BCG_ERR_INVALID, "CG / SCG take one right-hand side: context has N_rhs=%d", c->N);
+  if (c->nranks != 1 || c->ndim != 1) return fail(c, BCG_ERR_INVALID, "CG / SCG: single-rank 1-D contexts only");
+  if (!xh || !valid(c, b) || n_shifts < 1 || n_shifts > c->S)
+    return fail(c, BCG_ERR_INVALID, "bad argument (n_shifts=%d, context max %d)", n_shifts, c->S);
+  for (int s = 0; s < n_shifts; ++s)
+    if (!valid(c, xh[s]) || xh[s] == b) return fail(c, BCG_ERR_INVALID, "bad solution handle for shift %d", s);
+  if (sigma) {  // src/standard_solvers.cpp:38-42 (asserts in the reference)
+    if (sigma[0] < 0.0) return fail(c, BCG_ERR_INVALID, "shifts must be zero or positive");
+    for (int s = 1; s < n_shifts; ++s)
+      if (sigma[s] < sigma[s - 1]) return fail(c, BCG_ERR_INVALID, "shifts must be in ascending order");
+  }
+  if (!c->links_set) return fail(c, BCG_ERR_INVALID, "bcg_set_links has not been called");
+  CU(cudaSetDevice(c->device));
+  int r = ensure_work(c, n_shifts);
+  if (r) return r;
+  c->L.pair = 0;
+  r = init_ctrl(c, n_shifts, sigma, eps, eps_shifts, max_it);
+  if (r) return r;
+  int64_t launches = 0;
+  int l = 0;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  // x_s = 0 ; p_s = r = b ; r2 = r.r   (:6-11, :47-55)
+  for (int s = 0; s < n_shifts; ++s) CU(cudaMemsetAsync(c->fields[xh[s]], 0, field_elems(c) * sizeof(cd), c->stream));
+  CU(cudaMemcpyAsync(c->fields[c->work_Q], c->fields[b], field_elems(c) * sizeof(cd), cudaMemcpyDeviceToDevice,
+                     c->stream));
+  cd* R = fptr(c, c->work_Q);
+  int np = c->ops->gram(c->stream, R, R, c->V, c->gpart, nullptr, c->sms, &l);
+  KL(np);
+  scg_init_kernel<<<1, kScalarThreads, 0, c->stream>>>(c->gpart, np, c->ctrl);
+  ++l;
+  CU(cudaGetLastError());
+  LoopPlan p;
+  std::memset(&p, 0, sizeof p);
+  p.kind = 2;
+  p.n_shifts = n_shifts;
+  p.T = fptr(c, c->work_T);
+  p.Q = R;
+  p.sigma0 = sigma ? sigma[0] : 0.0;
+  for (int s = 0; s < n_shifts; ++s) {
+    CU(cudaMemcpyAsync(c->fields[c->work_P[s]], c->fields[b], field_elems(c) * sizeof(cd), cudaMemcpyDeviceToDevice,
+                       c->stream));
+    p.fp.X[s] = fptr(c, xh[s]);
+    p.fp.P[s] = fptr(c, c->work_P[s]);
+  }
+  p.P0 = p.fp.P[0];
+  r = halo_refresh(c, p.P0, 3 * c->N, c->ctrl, &l);
+  if (r) return r;
+  launches += l;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  if (info) std::memset(info, 0, sizeof *info);
+  if (max_it > 0) {
+    r = run_loop(c, p, info, &launches);  // an empty loop (b = 0, eps >= 1) is caught by scg_init_kernel's `done`
+    if (r) return r;
+  } else {
+    CU(cudaEventRecord(c->ev[2], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (info) info->residual = 1.0;
+  }
+  return finish_info(c, info, launches);
+}
+
 int ensure_host_handles(bcg_ctx* c, int n_shifts) {
   if (c->host_B < 0) {
     int r = field_alloc(c, &c->host_B);
@@ -1186,6 +1357,107 @@ int bcg_solve_sbcgrq(bcg_ctx* c, double* const* x_host, const double* b_host, co
     return r;
   for (int s = 0; s < n_shifts; ++s)
     if ((r = bcg_field_download(c, c->host_X[s], x_host[s]))) return r;
+  return BCG_OK;
+}
+
+// ---- CG / SCG: the reference's one-right-hand-side solvers (src/standard_solvers.cpp:3-95) ----------
+int bcg_solve_cg_dev(bcg_ctx* c, int x, int b, double eps, int max_it, bcg_solve_info* info) {
+  const double zero = 0.0;
+  return solve_scg(c, &x, b, &zero, 1, eps, 0.0, max_it, info);
+}
+int bcg_solve_scg_dev(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts, double eps,
+                      double eps_shifts, int max_it, bcg_solve_info* info) {
+  if (!sigma) return fail(c, BCG_ERR_INVALID, "sigma is null");
+  return solve_scg(c, xh, b, sigma, n_shifts, eps, eps_shifts, max_it, info);
+}
+int bcg_solve_cg(bcg_ctx* c, double* x_host, const double* b_host, double eps, int max_it, bcg_solve_info* info) {
+  if (!c || !x_host || !b_host) return fail(c, BCG_ERR_INVALID, "null argument");
+  int r = ensure_host_handles(c, 1);
+  if (r) return r;
+  if ((r = bcg_field_upload(c, c->host_B, b_host))) return r;
+  if ((r = bcg_solve_cg_dev(c, c->host_X[0], c->host_B, eps, max_it, info))) return r;
+  return bcg_field_download(c, c->host_X[0], x_host);
+}
+int bcg_solve_scg(bcg_ctx* c, double* const* x_host, const double* b_host, const double* sigma, int n_shifts,
+                  double eps, double eps_shifts, int max_it, bcg_solve_info* info) {
+  if (!c || !x_host || !b_host || !sigma) return fail(c, BCG_ERR_INVALID, "null argument");
+  if (n_shifts < 1 || n_shifts > c->S) return fail(c, BCG_ERR_INVALID, "bad n_shifts=%d (context max %d)", n_shifts, c->S);
+  int r = ensure_host_handles(c, n_shifts);
+  if (r) return r;
+  if ((r = bcg_field_upload(c, c->host_B, b_host))) return r;
+  if ((r = bcg_solve_scg_dev(c, c->host_X.data(), c->host_B, sigma, n_shifts, eps, eps_shifts, max_it, info)))
+    return r;
+  for (int s = 0; s < n_shifts; ++s)
+    if ((r = bcg_field_download(c, c->host_X[s], x_host[s]))) return r;
+  return BCG_OK;
+}
+
+// ---- statistics of the last solve ------------------------------------------------------------------
+int bcg_last_solve_stats(bcg_ctx* c, bcg_solve_stats* out) {
+  if (!c || !out) return fail(c, BCG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->ctrl_host, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  const Ctrl& h = c->ctrl_host[0];
+  std::memset(out, 0, sizeof *out);
+  out->iterations = h.iter;
+  out->n_shifts = h.n_shifts;
+  out->paired = c->L.pair;
+  for (int a = 0; a <= BCG_MAX_SHIFTS; ++a) out->active_hist[a] = h.hist[a];
+  out->shift_update_field_passes = h.shift_passes;
+  for (int s2 = 0; s2 < BCG_MAX_SHIFTS; ++s2) out->resid_shift[s2] = h.resid_shift[s2];
+  out->resid_shift[0] = h.residual;
+  return BCG_OK;
+}
+
+int bcg_set_loop_profile(bcg_ctx* c, int n_iterations) {
+  if (!c || n_iterations < 0 || n_iterations > 4096) return fail(c, BCG_ERR_INVALID, "bad profile window");
+  c->prof_want = n_iterations;
+  return BCG_OK;
+}
+int bcg_get_loop_profile(bcg_ctx* c, double* ms_out, int* n_out) {
+  if (!c || !ms_out || !n_out) return fail(c, BCG_ERR_INVALID, "null argument");
+  for (int k = 0; k < 8; ++k) ms_out[k] = c->prof_ms[k];
+  *n_out = c->prof_n;
+  return BCG_OK;
+}
+
+// ---- unit-test entry points of the device N x N routines the loops use ------------------------------
+int bcg_small_inverse(bcg_ctx* c, const double* a_host, double* out_host, int pivot, int* info_out) {
+  if (!c || !a_host || !out_host) return fail(c, BCG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  int r = upload_mat(c, M_SCRATCH, a_host, 0);
+  if (r) return r;
+  int* d_info = reinterpret_cast<int*>(c->gred);  // N*N complex of scratch: room for one int
+  if (c->small_smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(small_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->small_smem));
+  small_inverse_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(mat(c, M_R2_OLD), mat(c, M_SCRATCH), c->N,
+                                                                        pivot, d_info);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->mat_host + c->L.nn(), mat(c, M_R2_OLD), c->L.nn() * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+  int info_h = 0;
+  CU(cudaMemcpyAsync(&info_h, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::memcpy(out_host, c->mat_host + c->L.nn(), c->L.nn() * sizeof(cd));
+  if (info_out) *info_out = info_h;
+  return BCG_OK;
+}
+int bcg_small_lu_solve(bcg_ctx* c, const double* a_host, const double* b_host, double* x_host) {
+  if (!c || !a_host || !b_host || !x_host) return fail(c, BCG_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  int r = upload_mat(c, M_SCRATCH, a_host, 0);
+  if (r) return r;
+  r = upload_mat(c, M_R2, b_host, 1);
+  if (r) return r;
+  if (c->small_smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(small_lu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->small_smem));
+  small_lu_solve_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(mat(c, M_R2_OLD), mat(c, M_SCRATCH),
+                                                                         mat(c, M_R2), c->N);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->mat_host + 2 * c->L.nn(), mat(c, M_R2_OLD), c->L.nn() * sizeof(cd), cudaMemcpyDeviceToHost,
+                     c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  std::memcpy(x_host, c->mat_host + 2 * c->L.nn(), c->L.nn() * sizeof(cd));
   return BCG_OK;
 }
 

@@ -87,7 +87,39 @@ struct Ctrl {
   double resid_shift[kMaxShifts];  // last shifted residual estimate
   double sigma[kMaxShifts];
   int n_act[2];                    // n_unconv of the last odd / even iteration ([iter & 1]; paired multishift update)
+  // ---- statistics of the solve (read back by bcg_last_solve_stats; nothing in the loop depends on them) ----
+  unsigned hist[kMaxShifts + 1];       // hist[a] = iterations that ran with a systems still being updated
+  unsigned long long shift_passes;     // field-sized passes (units of F = 48 N V bytes) the multishift update has moved
+  // ---- scalar coefficients of CG / SCG (src/standard_solvers.cpp:3-95), N_rhs = 1 only ----
+  double sc_r2, sc_r2_0, sc_alpha, sc_beta, sc_alpha_old, sc_beta_old;
+  double sc_zeta[kMaxShifts], sc_theta[kMaxShifts];
+  double sc_ax[kMaxShifts], sc_bp[kMaxShifts], sc_zr[kMaxShifts];  // per system: x += p*ax ; p = p*bp + r*zr
 };
+
+// What one launch of the multishift update does, as a function of the control block the B-step of
+// the same iteration has left behind.  mode 0: plain (Q, then every active system); 1: first of a
+// pair (Q kept as Qprev, system 0 only); 2: second of a pair (Q, Qprev, system 0, both updates of
+// the shifted systems).  Shared by the kernel (shift_pair.cuh) and by the B-step's byte accounting.
+struct ShiftLaunchPlan {
+  int mode, n1, n2;
+  // field-sized passes through HBM (reads + writes)
+  __host__ __device__ int passes() const {
+    if (mode == 1) return 3 + 4;                 // Q in, Q out, Qprev out ; X_0, P_0 in and out
+    if (mode == 2) return 3 + 4 + 4 * (n1 - 1);  // Q in, Q out, Qprev in ; system 0 ; shifted systems once for both updates
+    return 2 + 4 * n2;
+  }
+};
+__host__ __device__ inline ShiftLaunchPlan shift_launch_plan(bool paired, int iter, int stop, int n_unconv, int n_act_odd) {
+  ShiftLaunchPlan p;
+  const bool odd = (iter & 1) != 0;
+  p.n2 = n_unconv;
+  p.n1 = odd ? n_unconv : n_act_odd;  // systems active in the odd iteration of this pair
+  // nothing is deferred when the loop ends on this iteration or no shifted system is active any more
+  if (paired && odd && !stop && p.n1 > 1) p.mode = 1;
+  else if (paired && !odd && p.n1 > 1) p.mode = 2;
+  else p.mode = 0;
+  return p;
+}
 
 // ---- peer-memory exchange between the ranks of a slab decomposition (NVLink P2P) -------------
 // Every rank owns a communication buffer that all peers have mapped (CUDA IPC).  A producer

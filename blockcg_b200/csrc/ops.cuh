@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include "common.cuh"
 #include "field_kernels.cuh"
 #include "dirac_chain.cuh"
@@ -186,11 +187,19 @@ struct Ops {
   struct Caps {
     int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0;
   };
+  // Both the shared-memory opt-ins (cudaFuncSetAttribute) and the occupancy figures are per
+  // DEVICE: one slot per device ordinal, filled under a lock the first time a context of that
+  // device asks (contexts on several GPUs in one process, possibly from several host threads).
+  static constexpr int kMaxDevices = 64;
   static Caps& caps() {
-    static Caps c;
-    return c;
+    static Caps c[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return c[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
   }
   static void prepare(int sms) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     Caps& c = caps();
     if (c.dirac) return;
     if constexpr (FUSED) {

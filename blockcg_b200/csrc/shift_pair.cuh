@@ -82,18 +82,11 @@ shift_pair_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
   const int iter = ctrl->iter;
   const bool odd = (iter & 1) != 0;
   PairPlan plan;
-  plan.n2 = ctrl->n_unconv;
-  // nothing is deferred when the loop ends on this iteration or no shifted system is active any more
-  const int n1 = odd ? plan.n2 : ctrl->n_act[1];  // systems active in the odd iteration of this pair
-  if (odd && !ctrl->stop && n1 > 1) {
-    plan.mode = 1;
-    plan.n_items = 2;
-  } else if (!odd && n1 > 1) {
-    plan.mode = 2;
-    plan.n_items = 2 + n1;
-  } else {
-    plan.mode = 0;
-    plan.n_items = 1 + plan.n2;
+  {
+    const ShiftLaunchPlan lp = shift_launch_plan(true, iter, ctrl->stop, ctrl->n_unconv, ctrl->n_act[1]);
+    plan.mode = lp.mode;
+    plan.n2 = lp.n2;
+    plan.n_items = (lp.mode == 1) ? 2 : (lp.mode == 2) ? 2 + lp.n1 : 1 + lp.n2;
   }
   const cd* Acur = odd ? Aodd : Aeven;
   const cd* Bcur = odd ? Bodd : Beven;

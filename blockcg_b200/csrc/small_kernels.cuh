@@ -735,13 +735,20 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
       ctrl->n_unconv_b = ctrl->n_unconv;
       ctrl->n_act[iter & 1] = ctrl->n_unconv;
       // while (residual > eps && iter < max_iterations)  -- NaN ends the loop as in the reference
-      if (!(r > ctrl->eps) || iter >= ctrl->max_it) ctrl->stop = 1;
+      int stop = 0;
+      if (!(r > ctrl->eps) || iter >= ctrl->max_it) stop = 1;
       if (info >= 0) {
         ctrl->status = 3;
-        ctrl->stop = 1;
+        stop = 1;
       } else if (nan) {
         ctrl->status = 6;
       }
+      if (stop) ctrl->stop = 1;
+      // statistics: systems updated in this iteration, bytes the multishift launch that follows will move
+      const int na = ctrl->n_unconv;
+      ctrl->hist[na < 0 ? 0 : (na > kMaxShifts ? kMaxShifts : na)] += 1u;
+      ctrl->shift_passes += static_cast<unsigned long long>(
+          shift_launch_plan(L.pair != 0, iter, stop, na, ctrl->n_act[1]).passes());
     }
     return;
   }
@@ -868,6 +875,151 @@ bcg_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__
     ctrl->residual = r;
     if (!(r > ctrl->eps) || ctrl->iter >= ctrl->max_it) ctrl->stop = 1;
     if (nan) ctrl->status = 6;
+  }
+}
+
+
+// ---- unit-test entry points of the device small-matrix routines (bcg_small_*) ----------------
+// out = in^-1 by the loop's own Gauss-Jordan inverse (pivot != 0: row pivoting, as used for
+// beta_s^-1; 0: the pivot-free variant used for the Hermitian positive definite P0^dag T).
+__global__ void __launch_bounds__(kSmallThreads)
+small_inverse_kernel(cd* __restrict__ out, const cd* __restrict__ in, int N, int pivot, int* __restrict__ info_out) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  SmallSmem s;
+  s.carve(raw, N);
+  sm_init_ij(N);
+  sm_copy(s.mat[0], in, N * N);
+  if (pivot) sm_inverse<true>(s.mat[0], s.mat[1], N, s.lw.rt, s.info);
+  else sm_inverse<false>(s.mat[0], s.mat[1], N, s.lw.rt, s.info);
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) out[e] = s.mat[0][e];
+  if (threadIdx.x == 0) *info_out = *s.info;
+}
+// X = A^-1 B by the Eigen-faithful full-pivoting LU of the BCG loop (FullPivLU.h:487-590,745-790)
+__global__ void __launch_bounds__(kSmallThreads)
+small_lu_solve_kernel(cd* __restrict__ X, const cd* __restrict__ A, const cd* __restrict__ B, int N) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  SmallSmem s;
+  s.carve(raw, N);
+  sm_init_ij(N);
+  sm_copy(s.mat[0], A, N * N);
+  sm_copy(s.mat[1], B, N * N);
+  sm_lu_solve(s.mat[1], s.mat[0], s.lw, N);
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) X[e] = s.mat[1][e];
+}
+
+// ---- CG / SCG: the reference's scalar-coefficient solvers for one right-hand side --------------
+// (src/standard_solvers.cpp:3-32 and :34-95).  Same device-resident loop as the block solvers --
+// stencil with fused p.t, r -= t alpha with fused r.r, one streaming update of all systems -- but
+// the coefficients are real scalars kept in the control block: no N x N algebra at all.
+// real_dot(a, b) = sum_x Re(a[x]^dag b[x]) (fields.hpp:93-100) = real part of the 1 x 1 Gram.
+__device__ __forceinline__ double sc_reduce_real(const cd* __restrict__ gpart, int nparts, double* red) {
+  double sum = 0.0;
+  for (int p = threadIdx.x; p < nparts; p += blockDim.x) sum += gpart[p].x;  // N = 1: one complex per partial
+  red[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {  // fixed tree: deterministic
+    if (static_cast<int>(threadIdx.x) < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  return red[0];
+}
+constexpr int kScalarThreads = 256;
+// init: r2 = r.r ; alpha = 1, beta = 0, zeta = theta = 1 (:13-14,50-53) ; eps *= sqrt(r2) is kept as r2_0
+__global__ void __launch_bounds__(kScalarThreads)
+scg_init_kernel(const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl) {
+  __shared__ double red[kScalarThreads];
+  const double r2 = sc_reduce_real(gpart, nparts, red);
+  if (threadIdx.x == 0) {
+    ctrl->sc_r2 = r2;
+    ctrl->sc_r2_0 = r2;
+    ctrl->sc_alpha = 1.0;
+    ctrl->sc_beta = 0.0;
+    for (int s = 0; s < kMaxShifts; ++s) ctrl->sc_zeta[s] = ctrl->sc_theta[s] = 1.0;
+    ctrl->residual = 1.0;
+    // while (sqrt(r2) > eps * sqrt(r2_0) && iter < max_iterations): may already be false (b = 0)
+    if (!(sqrt(r2) > ctrl->eps * sqrt(r2)) || ctrl->max_it <= 0) ctrl->done = 1;
+  }
+}
+// A-step: alpha = r2 / p0.t ; -alpha is the operand of r -= t alpha
+__global__ void __launch_bounds__(kScalarThreads)
+scg_step_a_kernel(cd* __restrict__ neg_alpha, const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl) {
+  if (ctrl->done) return;
+  if (ctrl->stop) {
+    __syncthreads();
+    if (threadIdx.x == 0) ctrl->done = 1;
+    return;
+  }
+  __shared__ double red[kScalarThreads];
+  const double pt = sc_reduce_real(gpart, nparts, red);
+  if (threadIdx.x == 0) {
+    ctrl->iter += 1;
+    ctrl->sc_alpha_old = ctrl->sc_alpha;
+    const double alpha = ctrl->sc_r2 / pt;
+    ctrl->sc_alpha = alpha;
+    *neg_alpha = cmake(-alpha, 0.0);
+  }
+}
+// B-step: r2, beta, the shifted coefficients (:71-87) and the stopping tests (:57,89-92)
+__global__ void __launch_bounds__(kScalarThreads)
+scg_step_b_kernel(const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl) {
+  if (ctrl->done) return;
+  __shared__ double red[kScalarThreads];
+  const double r2 = sc_reduce_real(gpart, nparts, red);
+  if (threadIdx.x != 0) return;
+  const double r2_old = ctrl->sc_r2;
+  const double beta_old = ctrl->sc_beta, alpha = ctrl->sc_alpha, alpha_old = ctrl->sc_alpha_old;
+  const double beta = r2 / r2_old;
+  ctrl->sc_r2 = r2;
+  ctrl->sc_beta_old = beta_old;
+  ctrl->sc_beta = beta;
+  const int na = ctrl->n_unconv;
+  ctrl->sc_ax[0] = alpha;
+  ctrl->sc_bp[0] = beta;
+  ctrl->sc_zr[0] = 1.0;
+  for (int s = na - 1; s > 0; --s) {
+    double inv_theta = 1.0 + (ctrl->sigma[s] - ctrl->sigma[0]) * alpha;
+    inv_theta += beta_old * (alpha / alpha_old) * (1.0 - ctrl->sc_theta[s]);
+    const double theta = 1.0 / inv_theta;
+    ctrl->sc_theta[s] = theta;
+    const double zeta = ctrl->sc_zeta[s] * theta;
+    ctrl->sc_zeta[s] = zeta;
+    ctrl->sc_ax[s] = alpha * theta;
+    ctrl->sc_bp[s] = beta * theta * theta;
+    ctrl->sc_zr[s] = zeta;
+  }
+  ctrl->n_act[0] = na;  // the update kernel of this iteration serves `na` systems ...
+  ctrl->hist[na < 0 ? 0 : (na > kMaxShifts ? kMaxShifts : na)] += 1u;
+  ctrl->shift_passes += static_cast<unsigned long long>(1 + 4 * na);
+  // ... and the highest one is dropped from the next iteration on once its residual is small enough
+  if (sqrt(r2) * ctrl->sc_zeta[na - 1] < ctrl->eps_shifts) ctrl->n_unconv = na - 1;
+  const double rel = sqrt(r2) / sqrt(ctrl->sc_r2_0);
+  ctrl->residual = rel;
+  if (!(sqrt(r2) > ctrl->eps * sqrt(ctrl->sc_r2_0)) || ctrl->iter >= ctrl->max_it) ctrl->stop = 1;
+  if (rel != rel) ctrl->status = 6;
+}
+// x_s += p_s ax_s ; p_s = p_s bp_s + r zr_s for the systems served in this iteration (:65-87): one
+// streaming pass, r read once.  n = complex numbers per field (3 V).
+struct ScalarPtrs {
+  cd* X[kMaxShifts];
+  cd* P[kMaxShifts];
+};
+static __global__ void __launch_bounds__(256)
+scg_update_kernel(ScalarPtrs fp, const cd* __restrict__ r, long long n, const Ctrl* __restrict__ ctrl) {
+  if (ctrl->done) return;
+  const int na = ctrl->n_act[0];
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const cd rv = r[i];
+    for (int s = 0; s < na; ++s) {
+      const double ax = ctrl->sc_ax[s], bp = ctrl->sc_bp[s], zr = ctrl->sc_zr[s];
+      const cd p = fp.P[s][i];
+      cd x = fp.X[s][i];
+      x.x += p.x * ax;  // this += rhs * scalar (fields.hpp:70-77)
+      x.y += p.y * ax;
+      fp.X[s][i] = x;
+      // tmp = this * lhs ; tmp += rhs * rhs_multiplier (fields.hpp:85-86)
+      fp.P[s][i] = cmake(p.x * bp + rv.x * zr, p.y * bp + rv.y * zr);
+    }
   }
 }
 

@@ -110,6 +110,30 @@ struct small_matrix {
       for (int c = 0; c < C; ++c) m(c, r) = std::conj((*this)(r, c));
     return m;
   }
+  // the expression forms the reference's callers write: -alpha, (beta * rho.adjoint()).eval(), 2.0 * M
+  small_matrix operator-() const {
+    small_matrix m;
+    for (int i = 0; i < R * C; ++i) m.a[i] = -a[i];
+    return m;
+  }
+  template <int C2>
+  small_matrix<R, C2> operator*(const small_matrix<C, C2>& o) const {
+    small_matrix<R, C2> m;
+    m.setZero();
+    for (int c = 0; c < C2; ++c)
+      for (int k = 0; k < C; ++k)
+        for (int r = 0; r < R; ++r) m(r, c) += (*this)(r, k) * o(k, c);
+    return m;
+  }
+  small_matrix operator*(double s) const {
+    small_matrix m;
+    for (int i = 0; i < R * C; ++i) m.a[i] = a[i] * s;
+    return m;
+  }
+  friend small_matrix operator*(double s, const small_matrix& m) { return m * s; }
+  small_matrix operator+(const small_matrix& o) const { return small_matrix(*this) += o; }
+  small_matrix operator-(const small_matrix& o) const { return small_matrix(*this) -= o; }
+  const small_matrix& eval() const { return *this; }
   small_matrix& operator+=(const small_matrix& o) {
     for (int i = 0; i < R * C; ++i) a[i] += o.a[i];
     return *this;
@@ -197,6 +221,10 @@ class block_fermion_field {  // inc/fields.hpp:25-147
     bcg_host::check(c, bcg_rescale_add(c, d.h, reinterpret_cast<const double*>(L.data()), s.h, r), "bcg_rescale_add");
     d.download(raw());
     return *this;
+  }
+  // scalar left multiplier, as dirac_op.hpp:42 (lhs.rescale_add(-1.0, rhs, mass * mass)) and CG / SCG use it
+  block_fermion_field<N_rhs>& rescale_add(double l, const block_fermion_field<N_rhs>& rhs, double r) {
+    return rescale_add(block_matrix<N_rhs>::Identity() * l, rhs, r);
   }
   // Re(this . rhs) for N_rhs == 1 (inc/fields.hpp:93-99): diagonal of the 1x1 Gram
   double real_dot(const block_fermion_field<1>& rhs) const {

@@ -4,6 +4,7 @@ Same names, argument meaning and return value as inc/block_solvers.hpp:
     BCG(X, B, D, eps=1e-15, max_iterations=1e6)            -> iterations   (:10-45)
     BCGrQ(X, B, D, eps=1e-15, max_iterations=1e6)          -> iterations   (:50-86)
     SBCGrQ(X, B, D, sigma, eps=1e-15, eps_shifts=1e-15, max_iterations=1e6) (:91-185)
+and of inc/standard_solvers.hpp (CG, SCG for one right-hand side; src/standard_solvers.cpp:3-95).
 `X` is overwritten (solvers start from 0), `B`, `D` are not modified, and the
 return value is the number of operator applications.  Fields are numpy
 complex128 arrays of shape (V, N, 3) in the reference's memory order; the
@@ -112,6 +113,35 @@ def SBCGrQ(X, B, D, sigma, eps=1e-15, eps_shifts=1e-15, max_iterations=int(1e6),
     ctx = _context(B.shape[0], B.shape[1], len(sigma), device)
     ctx.set_links(D.links, D.mass)
     r = ctx.solve_sbcgrq(list(X), np.ascontiguousarray(B), sigma, eps, eps_shifts, int(max_iterations))
+    if info is not None:
+        info.update(r.as_dict())
+    return r.iterations
+
+
+def CG(x, b, D, eps=1e-15, max_iterations=int(1e6), device=0, info=None):
+    """src/standard_solvers.cpp:3-32 (inc/standard_solvers.hpp:10-13): fields of shape (V, 1, 3)."""
+    _check(x, b)
+    if b.shape[1] != 1:
+        raise TypeError("CG takes one right-hand side: b must have shape (V, 1, 3)")
+    ctx = _context(b.shape[0], 1, 1, device)
+    ctx.set_links(D.links, D.mass)
+    r = ctx.solve_cg(x, np.ascontiguousarray(b), eps, int(max_iterations))
+    if info is not None:
+        info.update(r.as_dict())
+    return r.iterations
+
+
+def SCG(x, b, D, sigma, eps=1e-15, eps_shifts=1e-15, max_iterations=int(1e6), device=0, info=None):
+    """src/standard_solvers.cpp:34-95 (inc/standard_solvers.hpp:15-20)."""
+    if len(x) != len(sigma):
+        raise ValueError("number of shifts does not match number of solution vectors")
+    for xs in x:
+        _check(xs, b)
+    if b.shape[1] != 1:
+        raise TypeError("SCG takes one right-hand side: b must have shape (V, 1, 3)")
+    ctx = _context(b.shape[0], 1, len(sigma), device)
+    ctx.set_links(D.links, D.mass)
+    r = ctx.solve_scg(list(x), np.ascontiguousarray(b), sigma, eps, eps_shifts, int(max_iterations))
     if info is not None:
         info.update(r.as_dict())
     return r.iterations

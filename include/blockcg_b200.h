@@ -162,6 +162,53 @@ int bcg_solve_bcgrq(bcg_ctx* ctx, double* x_host, const double* b_host, double e
 int bcg_solve_sbcgrq(bcg_ctx* ctx, double* const* x_host, const double* b_host, const double* sigma,
                      int n_shifts, double eps, double eps_shifts, int max_iterations, bcg_solve_info* info);
 
+/* ---- CG / SCG: the reference's solvers for ONE right-hand side (context with n_rhs = 1) ------
+ *   bcg_solve_cg   <- CG    src/standard_solvers.cpp:3-32    (inc/standard_solvers.hpp:10-13)
+ *   bcg_solve_scg  <- SCG   src/standard_solvers.cpp:34-95   (inc/standard_solvers.hpp:15-20)
+ * Scalar recurrences (alpha, beta, zeta_s, theta_s) evaluated on the device exactly as the reference
+ * writes them; stopping rule |r| > eps |b| on the lowest shift, a shifted system is dropped once
+ * |r| zeta_s < eps_shifts (NOT normalised by |b|, as in the reference, :89-92). */
+int bcg_solve_cg_dev(bcg_ctx* ctx, int x, int b, double eps, int max_iterations, bcg_solve_info* info);
+int bcg_solve_scg_dev(bcg_ctx* ctx, const int* x_handles, int b, const double* sigma, int n_shifts, double eps,
+                      double eps_shifts, int max_iterations, bcg_solve_info* info);
+int bcg_solve_cg(bcg_ctx* ctx, double* x_host, const double* b_host, double eps, int max_iterations,
+                 bcg_solve_info* info);
+int bcg_solve_scg(bcg_ctx* ctx, double* const* x_host, const double* b_host, const double* sigma, int n_shifts,
+                  double eps, double eps_shifts, int max_iterations, bcg_solve_info* info);
+
+/* ---- statistics of the last solve on this context (measurement; nothing the reference has) ---- */
+typedef struct {
+  int iterations;
+  int n_shifts;
+  int paired;                                    /* 1: shifted systems were served every second iteration */
+  uint32_t active_hist[BCG_MAX_SHIFTS + 1];      /* [a] = iterations in which a systems were still updated
+                                                    (block_solvers.hpp:161,179-181: shifts retire at eps_shifts) */
+  uint64_t shift_update_field_passes;            /* field-sized (48 N V bytes) reads + writes the multishift
+                                                    update kernels moved through HBM over the whole solve */
+  double resid_shift[BCG_MAX_SHIFTS];            /* last residual estimate per system ([0]: the stopping residual) */
+} bcg_solve_stats;
+int bcg_last_solve_stats(bcg_ctx* ctx, bcg_solve_stats* out);
+
+/* In-loop profile: the first n_iterations (<= 4096) of the NEXT solve on this context are submitted
+ * kernel by kernel with a CUDA event after each stage instead of as graph batches; the solve is otherwise
+ * unchanged.  bcg_get_loop_profile returns mean device milliseconds per iteration over the window:
+ * ms_out[0] stencil + fused Gram, [1] coefficient A-step, [2] Q update + fused Gram, [3] coefficient B-step,
+ * [4] multishift update of an ODD iteration, [5] of an EVEN iteration (paired update: shift_pair.cuh),
+ * [6] halo refresh, [7] whole iteration; *n_out = iterations in the window (0: no profile taken). */
+int bcg_set_loop_profile(bcg_ctx* ctx, int n_iterations);
+int bcg_get_loop_profile(bcg_ctx* ctx, double* ms_out /* [8] */, int* n_out);
+
+/* ---- unit-test entry points of the device N x N routines (isolated parity with Eigen) ----------
+ * bcg_small_inverse : out = a^-1 with the Gauss-Jordan inverse the (S)BCGrQ loops use in place of
+ *                     fullPivLu().solve(I) (block_solvers.hpp:142,166); pivot = 1: row pivoting (beta_s),
+ *                     0: pivot-free (Hermitian positive definite P^dag T).  *info_out = -1, or the column
+ *                     whose pivot vanished (no rank truncation: documented divergence from FullPivLU.h:317-341).
+ * bcg_small_lu_solve: x = a^-1 b with the Eigen-faithful full-pivoting LU of the BCG loop
+ *                     (block_solvers.hpp:31,36; FullPivLU.h:487-590,745-790, rank threshold included).
+ * Matrices N x N complex128 column-major on the host. */
+int bcg_small_inverse(bcg_ctx* ctx, const double* a_host, double* out_host, int pivot, int* info_out);
+int bcg_small_lu_solve(bcg_ctx* ctx, const double* a_host, const double* b_host, double* x_host);
+
 /* ---- micro-benchmark hooks (timed on the context's stream with CUDA events) -------------- */
 /* Runs `reps` back-to-back launches of one kernel and returns the mean device
  * time per launch in *ms_out.  which: 0 dirac apply (+fused Gram), 1 dirac apply only,

@@ -56,6 +56,16 @@ def main():
     np.savez_compressed(os.path.join(OUT, "solve_V64_N1.npz"), **solvers(64, 1, 0.5, 1e-10, TEST_SHIFTS))
     np.savez_compressed(os.path.join(OUT, "solve_V48_N4.npz"), **solvers(48, 4, 0.1, 1e-10, TEST_SHIFTS))
     np.savez_compressed(os.path.join(OUT, "solve_V40_N12.npz"), **solvers(40, 12, 0.05, 1e-10, BENCH_SHIFTS))
+    # CG / SCG (src/standard_solvers.cpp) at the reference's test configuration (test/solvers.cpp:8-17,19-51:
+    # V=128, mass 0.5, eps 1e-10, the five test shifts) and at a long-running one
+    r1 = RefShim(1)
+    for V, mass, shifts, tag in [(128, 0.5, TEST_SHIFTS, "V128"), (200, 0.01, BENCH_SHIFTS, "V200")]:
+        U, b = r1.make_inputs(V, 1)
+        xc, itc, _ = r1.CG(U, b, mass, 1e-10)
+        xs, its_, _ = r1.SCG(U, b, mass, shifts, 1e-10, 1e-15)
+        np.savez_compressed(os.path.join(OUT, "scalar_%s.npz" % tag), V=V, N=1, mass=mass, eps=1e-10, eps_shifts=1e-15,
+                            shifts=np.array(shifts, float), U=U, B=b, X_cg=xc, it_cg=itc, X_scg=xs, it_scg=its_)
+        print("%s: CG %d it, SCG %d it" % (tag, itc, its_))
     # README / benchmark default: ./benchmark 1e3 1e-3 1e-10 (README.md:29): keep it small --
     # iteration counts, per-shift true residuals and a strided sample of the solutions.
     V, N, mass, eps = 1000, 12, 1e-3, 1e-10

@@ -155,6 +155,24 @@ class Oracle:
                                  C.c_int(chunk), C.byref(sec), C.byref(nun))
         return X, it, sec.value, nun.value
 
+    def CG(self, U, b, mass, eps=1e-15, max_it=1000000):
+        V = b.shape[0]
+        assert b.shape == (V, 1, 3)
+        x = np.empty_like(b)
+        self.lib.ora_CG.restype = C.c_int
+        it = self.lib.ora_CG(C.c_int(V), C.c_double(mass), _p(U), _p(b), _p(x), C.c_double(eps), C.c_int(max_it))
+        return x, it
+
+    def SCG(self, U, b, mass, sigma, eps=1e-15, eps_shifts=1e-15, max_it=1000000):
+        V = b.shape[0]
+        assert b.shape == (V, 1, 3)
+        sig = np.ascontiguousarray(sigma, dtype=np.float64)
+        x = np.empty((len(sig), V, 1, 3), np.complex128)
+        self.lib.ora_SCG.restype = C.c_int
+        it = self.lib.ora_SCG(C.c_int(V), C.c_double(mass), _p(U), _p(b), _p(x), _p(sig), C.c_int(len(sig)),
+                              C.c_double(eps), C.c_double(eps_shifts), C.c_int(max_it))
+        return x, it
+
     def true_residual(self, U, B, X, mass, sigma=0.0):
         V, N, _ = B.shape
         out = np.empty(N, np.float64)
@@ -263,6 +281,28 @@ class RefShim:
         it = self._f("ref_SBCGrQ")(C.c_int(V), C.c_double(mass), _p(U), _p(B), _p(X), _p(sig), C.c_int(S),
                                    C.c_double(eps), C.c_double(eps_shifts), C.c_int(max_it), C.byref(sec))
         return X, it, sec.value
+
+
+    def CG(self, U, b, mass, eps=1e-15, max_it=1000000):
+        assert self.N == 1
+        V = b.shape[0]
+        x = np.empty_like(b)
+        sec = C.c_double(0)
+        self.lib.ref_CG_1.restype = C.c_int
+        it = self.lib.ref_CG_1(C.c_int(V), C.c_double(mass), _p(U), _p(b), _p(x), C.c_double(eps), C.c_int(max_it),
+                               C.byref(sec))
+        return x, it, sec.value
+
+    def SCG(self, U, b, mass, sigma, eps=1e-15, eps_shifts=1e-15, max_it=1000000):
+        assert self.N == 1
+        V = b.shape[0]
+        sig = np.ascontiguousarray(sigma, dtype=np.float64)
+        x = np.empty((len(sig), V, 1, 3), np.complex128)
+        sec = C.c_double(0)
+        self.lib.ref_SCG_1.restype = C.c_int
+        it = self.lib.ref_SCG_1(C.c_int(V), C.c_double(mass), _p(U), _p(b), _p(x), _p(sig), C.c_int(len(sig)),
+                                C.c_double(eps), C.c_double(eps_shifts), C.c_int(max_it), C.byref(sec))
+        return x, it, sec.value
 
 
 def counter_uniform(seed, stream, first, n):

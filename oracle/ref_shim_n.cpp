@@ -28,6 +28,9 @@
 #include "dirac_op.hpp"
 #undef private
 #include "block_solvers.hpp"
+#if NRHS == 1
+#include "standard_solvers.hpp"  // CG / SCG: compiled from the reference's own src/standard_solvers.cpp (Makefile)
+#endif
 
 #ifndef NRHS
 #error "compile with -DNRHS=<n>"
@@ -195,5 +198,35 @@ int FN(ref_SBCGrQ)(int V, double mass, const double* U, const double* B, double*
   for (int s = 0; s < n_shifts; ++s) store_field(x[s], X + static_cast<size_t>(s) * 2 * 3 * N * V);
   return it;
 }
+
+#if NRHS == 1
+// CG / SCG exist for one right-hand side only (inc/standard_solvers.hpp:10-20)
+int ref_CG_1(int V, double mass, const double* U, const double* B, double* X, double eps, int max_it,
+             double* seconds) {
+  dirac_op D(V, mass);
+  load_links(D, U);
+  field_t b(V), x(V);
+  load_field(b, B);
+  double t0 = now();
+  int it = CG(x, b, D, eps, max_it);
+  *seconds = now() - t0;
+  store_field(x, X);
+  return it;
+}
+int ref_SCG_1(int V, double mass, const double* U, const double* B, double* X, const double* sigma, int n_shifts,
+              double eps, double eps_shifts, int max_it, double* seconds) {
+  dirac_op D(V, mass);
+  load_links(D, U);
+  field_t b(V);
+  load_field(b, B);
+  std::vector<field_t> x(n_shifts, b);
+  std::vector<double> sig(sigma, sigma + n_shifts);
+  double t0 = now();
+  int it = SCG(x, b, D, sig, eps, eps_shifts, max_it);
+  *seconds = now() - t0;
+  for (int s = 0; s < n_shifts; ++s) store_field(x[s], X + static_cast<size_t>(s) * 2 * 3 * V);
+  return it;
+}
+#endif
 
 }  // extern "C"

@@ -386,3 +386,162 @@ def test_error_paths(bcg):
         assert ctx.solve_bcg_dev(hx, hb, 1e-10, 0).iterations == 0
         assert ctx.solve_bcg_dev(hx, hb, 2.0, 100).iterations == 0
         assert np.all(ctx.download(hx) == 0)
+
+
+# ---- round 2 ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", PRIMS)
+def test_device_small_matrix_routines_vs_golden(bcg, oracle, name):
+    """The device N x N routines in isolation against Eigen's own outputs (fixtures `lu_inv_M`,
+    `lu_inv_G`: fullPivLu().solve(I) of the unmodified reference, block_solvers.hpp:142,166) --
+    the Gauss-Jordan inverse the (S)BCGrQ loops use (row-pivoted: general M; pivot-free: the Hermitian
+    positive definite Gram G) and the Eigen-faithful full-pivot LU solve of the BCG loop.
+    Tolerance: 1e-11 * cond-like growth; both are backward stable, the elimination order differs."""
+    g = golden(name)
+    N = int(g["N"])
+    M, G = g["M"], g["gram_B_AB"]
+    with bcg.Context(8, N) as ctx:
+        for A, want, pivot in ((M, g["lu_inv_M"], True), (G, g["lu_inv_G"], True), (G, g["lu_inv_G"], False)):
+            if np.linalg.cond(A) > 1e8:   # V < N fixtures: the Gram is singular, Eigen truncates -- documented divergence
+                continue
+            inv, info = ctx.small_inverse(A, pivot)
+            assert info == -1
+            assert rel(inv, want) < 1e-11 * max(1.0, np.linalg.cond(A) / 100), (name, pivot)
+            assert np.abs(inv @ A - np.eye(N)).max() < 1e-12 * np.linalg.cond(A)
+        if np.linalg.cond(M) < 1e8:
+            X = ctx.small_lu_solve(M, G)
+            assert rel(X, oracle.fullpivlu_solve(M, G)) < 1e-12 * max(1.0, np.linalg.cond(M) / 100)
+            assert rel(ctx.small_lu_solve(M, np.eye(N)), g["lu_inv_M"]) < 1e-12 * max(1.0, np.linalg.cond(M) / 100)
+        # a singular matrix is reported, not silently inverted
+        Z = np.zeros((N, N), complex)
+        _, info = ctx.small_inverse(Z, True)
+        assert info >= 0
+
+
+@pytest.mark.parametrize("name", ["scalar_V128.npz", "scalar_V200.npz"])
+def test_cg_scg_vs_golden(bcg, name):
+    """CG / SCG (src/standard_solvers.cpp:3-95) with scalar recurrences on the device against the
+    unmodified reference's own CG / SCG (fixtures from oracle/gen_golden.py): iterations +-1,
+    solutions <= 1e-9 per shift, the reference's test rule true residual < 2 eps (test/solvers.cpp:30,49)."""
+    g = golden(name)
+    V, mass, eps = int(g["V"]), float(g["mass"]), float(g["eps"])
+    U, b, shifts = g["U"], g["B"], list(g["shifts"])
+    D = bcg.dirac_op(V, mass, links=U)
+    x = np.empty_like(b)
+    info = {}
+    it = bcg.CG(x, b, D, eps, info=info)
+    assert abs(it - int(g["it_cg"])) <= 1
+    assert rel(x, g["X_cg"]) < 1e-9
+    assert info["kernel_launches"] > 0
+    xs = [np.empty_like(b) for _ in shifts]
+    it = bcg.SCG(xs, b, D, shifts, eps, float(g["eps_shifts"]))
+    assert abs(it - int(g["it_scg"])) <= 1
+    with bcg.Context(V, 1) as ctx:
+        ctx.set_links(U, mass)
+        hb, hx = ctx.field(b), ctx.field()
+        for s, sig in enumerate(shifts):
+            assert rel(xs[s], g["X_scg"][s]) < 1e-9
+            ctx.upload(hx, xs[s])
+            assert ctx.true_residual(hx, hb, sig).max() < 2 * eps
+    # SCG drops converged shifts: with a loose eps_shifts the high shifts retire early and their solutions
+    # stop improving, exactly as the reference's (iteration counts are not affected, :57)
+    xs2 = [np.empty_like(b) for _ in shifts]
+    it2 = bcg.SCG(xs2, b, D, shifts, eps, 1e-4)
+    assert it2 == it
+    assert np.array_equal(xs2[0], xs[0])
+
+
+def test_cg_scg_longer_vs_oracle(bcg, oracle):
+    V, mass, eps = 5000, 0.05, 1e-10
+    shifts = [0.0, 1e-4, 1e-2, 0.5]
+    U, b = oracle.make_inputs(V, 1, 9)
+    D = bcg.dirac_op(V, mass, links=U)
+    x = np.empty_like(b)
+    it = bcg.CG(x, b, D, eps)
+    xo, ito = oracle.CG(U, b, mass, eps)
+    assert abs(it - ito) <= max(1, ito // 100) and rel(x, xo) < 1e-9
+    xs = [np.empty_like(b) for _ in shifts]
+    it = bcg.SCG(xs, b, D, shifts, eps, 1e-12)
+    xso, itso = oracle.SCG(U, b, mass, shifts, eps, 1e-12)
+    assert abs(it - itso) <= max(1, itso // 100)
+    for s in range(len(shifts)):
+        assert rel(xs[s], xso[s]) < 1e-9
+    with pytest.raises(bcg.BcgError):  # CG is defined for one right-hand side
+        with bcg.Context(64, 3) as ctx:
+            ctx.set_links(np.zeros((64, 3, 3), complex), 0.5)
+            ctx.solve_cg(np.zeros((64, 3, 3), complex), np.ones((64, 3, 3), complex), 1e-10)
+
+
+def test_cached_context_follows_the_operator(bcg, oracle):
+    """Two solves on ONE cached device context with operators of different mass: the captured
+    iteration graph bakes m^2 in by value and must be rebuilt (regression: it used to replay the
+    old graph and converge to the old-mass solution)."""
+    V, N, eps = 600, 4, 1e-10
+    U, B = oracle.make_inputs(V, N, 4)
+    for mass in (0.5, 0.1, 0.5):
+        D = bcg.dirac_op(V, mass, links=U)
+        X = np.empty_like(B)
+        bcg.BCGrQ(X, B, D, eps)
+        assert oracle.true_residual(U, B, X, mass, 0.0).max() < 2 * eps, mass
+        Xs = [np.empty_like(B) for _ in range(3)]
+        bcg.SBCGrQ(Xs, B, D, [0.0, 0.01, 0.3], eps, 1e-15)
+        for s, sig in enumerate([0.0, 0.01, 0.3]):
+            assert oracle.true_residual(U, B, Xs[s], mass, sig).max() < 2 * eps, (mass, sig)
+
+
+def test_solve_statistics(bcg, oracle):
+    """bcg_last_solve_stats: the active-system histogram sums to the iteration count, follows the
+    reference's retirement rule (block_solvers.hpp:161,179-181: highest shifts first) and the byte
+    accounting of the multishift update matches the launch plan."""
+    V, N, mass, eps = 1000, 12, 0.02, 1e-10
+    shifts = [0.0, 1e-4, 1e-2, 0.1, 0.5, 0.9]
+    U, B = oracle.make_inputs(V, N, 5)
+    for pair in ("0", "1"):
+        os.environ["BCG_PAIR"] = pair
+        try:
+            with bcg.Context(V, N, max_shifts=len(shifts)) as ctx:
+                ctx.set_links(U, mass)
+                hb = ctx.field(B)
+                xs = [ctx.field() for _ in shifts]
+                info = ctx.solve_sbcgrq_dev(xs, hb, shifts, eps, 1e-9)
+                st = ctx.last_solve_stats()
+        finally:
+            del os.environ["BCG_PAIR"]
+        h = st["active_hist"]
+        assert sum(h) == info.iterations == st["iterations"]
+        assert h[len(shifts)] > 0 and sum(h[len(shifts) + 1:]) == 0 and h[0] == 0
+        assert st["paired"] == (pair == "1")
+        plain = sum((2 + 4 * a) * n for a, n in enumerate(h))
+        if pair == "0":
+            assert st["shift_update_field_passes"] == plain
+        else:   # shifted systems touched once per two iterations: fewer passes than the plain loop
+            assert 0.5 * plain < st["shift_update_field_passes"] < plain
+        assert st["resid_shift"][0] == info.residual
+
+
+def test_headline_volume_lockstep_vs_reference(bcg, oracle):
+    """BASELINE configs[2] size (24^4 sites, N = 12, the nine benchmark shifts, mass 1e-3): K = 4
+    iterations of the GPU loop against 4 iterations of the UNMODIFIED reference (oracle/_ref when it
+    travelled, else the oracle port) on the same inputs -- every shift's X <= 1e-10 relative -- and
+    size-independent properties of the full-size operator."""
+    from oracle.pyoracle import RefShim
+    V, N, mass, K = 24 ** 4, 12, 1e-3, 4
+    shifts = [0, 0, 1e-10, 1e-8, 1e-6, 1e-5, 1e-4, 1e-2, 1e-1]
+    rng = np.random.default_rng(1)
+    U = rng.uniform(-1, 1, (V, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 3, 3))
+    B = rng.uniform(-1, 1, (V, N, 3)) + 1j * rng.uniform(-1, 1, (V, N, 3))
+    if RefShim.available(N):
+        Xr, itr, _ = RefShim(N).SBCGrQ(U, B, mass, shifts, 1e-10, 1e-15, max_it=K)
+    else:
+        Xr, itr, _, _ = oracle.SBCGrQ(U, B, mass, shifts, 1e-10, 1e-15, max_it=K)
+    assert itr == K
+    with bcg.Context(V, N, max_shifts=len(shifts)) as ctx:
+        ctx.set_links(U, mass)
+        hb = ctx.field(B)
+        xs = [ctx.field() for _ in shifts]
+        info = ctx.solve_sbcgrq_dev(xs, hb, shifts, 1e-10, 1e-15, K)
+        assert info.iterations == K
+        for s in range(len(shifts)):
+            assert rel(ctx.download(xs[s]), Xr[s]) < 1e-10, s
+        ha = ctx.field()
+        G = ctx.op(ha, hb, want_gram=True)
+        assert np.abs(G - G.conj().T).max() / np.abs(G).max() < 1e-13 and np.all(G.diagonal().real > 0)

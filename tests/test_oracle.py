@@ -179,3 +179,19 @@ def test_counter_uniform_generator():
     assert int(z) == 0xE220A8397B1DCDAF
     assert ora.counter_uniform(0, 0, 0, 1)[0] == float(int(z) >> 11) * 2.0 ** -52 - 1.0
 
+
+
+@pytest.mark.parametrize("name", ["scalar_V128.npz", "scalar_V200.npz"])
+def test_oracle_cg_scg_vs_golden(oracle, name):
+    """CG / SCG restatement (oracle.cpp: ora_CG / ora_SCG) against the unmodified reference's own CG / SCG
+    (src/standard_solvers.cpp, linked into oracle/_ref/libref_n1.so; fixtures from gen_golden.py)."""
+    g = golden(name)
+    U, b, mass, eps = g["U"], g["B"], float(g["mass"]), float(g["eps"])
+    x, it = oracle.CG(U, b, mass, eps)
+    assert it == int(g["it_cg"])
+    assert np.abs(x - g["X_cg"]).max() / np.abs(g["X_cg"]).max() < 1e-12
+    xs, it = oracle.SCG(U, b, mass, list(g["shifts"]), eps, float(g["eps_shifts"]))
+    assert it == int(g["it_scg"])
+    for s in range(len(g["shifts"])):
+        assert np.abs(xs[s] - g["X_scg"][s]).max() / np.abs(g["X_scg"][s]).max() < 1e-12
+        assert oracle.true_residual(U, b, xs[s], mass, float(g["shifts"][s])).max() < 2 * eps
