@@ -474,15 +474,17 @@ def run_ours(args, w, wname):
     # SURVEY 8(d) x the units a launch processes: one back-substitution (2 F) and a system updates (4 F each).
     # "shift_pair[a]" is the AVERAGE launch of an odd + even pair (the loop serves the shifted systems every
     # second iteration, shift_pair.cuh); "shift_update[a]" the plain kernel (every system every iteration).
-    upd = "shift_pair" if paired else "shift_update"
+    dmma = os.environ.get("BCG_DMMA", "1") != "0" and N % 4 == 0   # shift_dmma.cuh: the same update on the FP64 tensor instruction
+    upd = ("shift_dmma_pair" if paired else "shift_dmma") if dmma else ("shift_pair" if paired else "shift_update")
+    plain = "shift_dmma" if dmma else "shift_update"
     t_upd = {}
     for a in range(1, S + 1):
         if paired:
-            t_upd[a] = bench("shift_pair[%d]" % a, 13, 1 + 2 * a, a, (2 + 4 * a) * F, 2, 12)
+            t_upd[a] = bench("%s[%d]" % (upd, a), 13, 1 + 2 * a, a, (2 + 4 * a) * F, 2, 12)
         else:
-            t_upd[a] = bench("shift_update[%d]" % a, 4, 1 + 2 * a, a, (2 + 4 * a) * F, 1, 12)
+            t_upd[a] = bench("%s[%d]" % (upd, a), 4, 1 + 2 * a, a, (2 + 4 * a) * F, 1, 12)
     if paired:
-        bench("shift_update[%d]" % S, 4, 1 + 2 * S, S, (2 + 4 * S) * F)  # for comparison
+        bench("%s[%d]" % (plain, S), 4, 1 + 2 * S, S, (2 + 4 * S) * F)  # every system every iteration: for comparison
     for h in hs[1:]:
         ctx.free(h)
     ctx.free(hb)

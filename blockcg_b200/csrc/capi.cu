@@ -410,7 +410,7 @@ int ensure_work(bcg_ctx* c, int n_shifts) {
     int r = field_alloc(c, &c->work_Q);
     if (r) return r;
   }
-  if (c->work_Qp < 0 && n_shifts > 1 && c->ops->shift_update_pair) {
+  if (c->work_Qp < 0 && n_shifts > 1 && (c->ops->shift_update_pair || c->ops->shift_update_dmma)) {
     int r = field_alloc(c, &c->work_Qp);
     if (r) return r;
   }
@@ -858,10 +858,17 @@ bool pair_default() {  // read per solve, so that a test can compare both paths 
   return e ? std::atoi(e) != 0 : true;
 }
 
+// The (S)BCGrQ update on the FP64 tensor instruction (shift_dmma.cuh).  BCG_DMMA=0 selects the DFMA kernels.
+bool dmma_default() {  // read per solve, so that a test can compare both paths in one process
+  const char* e = std::getenv("BCG_DMMA");
+  return e ? std::atoi(e) != 0 : true;
+}
+
 struct LoopPlan {
   int kind;  // 0 BCG, 1 (S)BCGrQ, 2 CG / SCG (scalar coefficients, N_rhs = 1)
   int n_shifts;
   bool pair;  // multishift loop with the paired update
+  bool dmma;  // (S)BCGrQ update by shift_dmma_kernel (plain or paired schedule)
   cd* P0;
   cd* T;
   cd* Q;  // BCG: R
@@ -945,7 +952,11 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   ++*launches;
   CU(cudaGetLastError());
   BCG_MARK(4);
-  if (p.pair)
+  if (p.dmma)
+    KL(c->ops->shift_update_dmma(c->stream, p.Q, p.pair ? fptr(c, c->work_Qp) : nullptr, &p.fp, mat(c, M_RHO_CUR),
+                                 c->mats + c->L.A(0, 1), c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0),
+                                 c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair ? 1 : 0));
+  else if (p.pair)
     KL(c->ops->shift_update_pair(c->stream, p.Q, fptr(c, c->work_Qp), &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1),
                                  c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0), c->mats + c->L.B(0, 0), c->V, c->ctrl,
                                  c->sms, launches));
@@ -977,6 +988,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     key.push_back(bits);
   }
   key.push_back(p.pair ? &c->work_Qp : nullptr);
+  key.push_back(p.dmma ? &c->work_Q : nullptr);
   GraphCache& g = c->graph;
   if (!g.exec || g.kind != p.kind || g.n_shifts != p.n_shifts || g.batch != batch || g.key != key) {
     if (g.exec) {
@@ -1122,7 +1134,8 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   if (r) return r;
   r = init_ctrl(c, n_shifts, sigma, eps, eps_shifts, max_it);
   if (r) return r;
-  const bool pair = pair_default() && n_shifts > 1 && c->ops->shift_update_pair != nullptr && c->work_Qp >= 0;
+  const bool pair = pair_default() && n_shifts > 1 && c->work_Qp >= 0 &&
+                    (c->ops->shift_update_pair != nullptr || (dmma_default() && c->ops->shift_update_dmma != nullptr));
   c->L.pair = pair ? 1 : 0;
   int64_t launches = 0;
   int l = 0;
@@ -1146,6 +1159,7 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   std::memset(&p, 0, sizeof p);
   p.kind = 1;
   p.pair = pair;
+  p.dmma = dmma_default() && c->ops->shift_update_dmma != nullptr;
   p.n_shifts = n_shifts;
   p.T = fptr(c, c->work_T);
   p.Q = Q;
@@ -1484,8 +1498,9 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   }
   MatLayout Lp = c->L;
   Lp.pair = 1;
-  if (which == 13) {  // paired multishift update: one repetition = an odd and an even iteration's launch
-    if (!c->ops->shift_update_pair) return fail(c, BCG_ERR_INVALID, "no paired multishift kernel at N=%d", c->N);
+  const bool use_dmma = dmma_default() && c->ops->shift_update_dmma != nullptr && (which == 13 || which == 4);
+  if (which == 13 || (which == 4 && use_dmma)) {  // paired multishift update: one repetition = an odd and an even iteration's launch
+    if (!c->ops->shift_update_pair && !use_dmma) return fail(c, BCG_ERR_INVALID, "no paired multishift kernel at N=%d", c->N);
     if (c->work_Qp < 0) {
       int r_ = field_alloc(c, &c->work_Qp);
       if (r_) return r_;
@@ -1504,10 +1519,16 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   auto body = [&](int* l) -> int {
     switch (which) {
       case 13:
-        for (int i = 0; i < 2; ++i)
-          KL(c->ops->shift_update_pair(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
-                                       c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
-                                       c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l));
+        for (int i = 0; i < 2; ++i) {
+          if (use_dmma)
+            KL(c->ops->shift_update_dmma(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
+                                         c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
+                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l, 1));
+          else
+            KL(c->ops->shift_update_pair(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
+                                         c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
+                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l));
+        }
         break;
       case 0: {
         int np_ = 0;
@@ -1543,6 +1564,12 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
                              c->sms, l, nullptr));
         break;
       case 4:
+        if (use_dmma) {  // every system every iteration, on the tensor-instruction kernel
+          KL(c->ops->shift_update_dmma(c->stream, fptr(c, h[0]), nullptr, &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
+                                       c->mats + c->L.B(0), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
+                                       c->bench_ctrl, c->sms, l, 0));
+          break;
+        }
         KL(c->ops->shift_update(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
                                 c->mats + c->L.B(0), c->V, 1, n_shifts, nullptr, c->sms, l));
         break;

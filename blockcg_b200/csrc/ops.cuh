@@ -9,6 +9,7 @@
 #include "axpy_pipe.cuh"
 #include "dirac4d.cuh"
 #include "shift_pair.cuh"
+#include "shift_dmma.cuh"
 
 namespace bcg {
 
@@ -52,6 +53,11 @@ struct OpsTable {
   int (*shift_update_pair)(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                            const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
                            int sms, int* launches);
+  // the same update (plain or paired schedule) on the FP64 tensor instruction (shift_dmma.cuh); nullptr
+  // where it is not built (N not a multiple of 4).  paired = 0: every system every iteration.
+  int (*shift_update_dmma)(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
+                           const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
+                           int sms, int* launches, int paired);
   int (*max_partials)(int sms);
   // sites that must be allocated after site 0 of every field / of the links (>= V + 2): the
   // tensor-map views of the chain stencil are rectangular and reach past the end of the field
@@ -173,6 +179,9 @@ struct Ops {
   static constexpr bool PIPE_OK = SG::SMEM_BYTES <= 227 * 1024 && 2 * SG::PAIR <= 256;
   using SPG = ShiftPairGeom<N, SHIFT_TS>;
   static constexpr bool PAIR_OK = PIPE_OK && SPG::SMEM_BYTES <= 227 * 1024;
+  static constexpr bool DMMA_N = (N % 4 == 0);
+  using SDG = ShiftDmmaGeom<DMMA_N ? N : 4, SHIFT_TS>;
+  static constexpr bool DMMA_OK = DMMA_N && SDG::SMEM_BYTES <= 227 * 1024 && 2 * SDG::PAIR <= 256;
   static constexpr bool APIPE = (N % 2 == 0 && N >= 4 && N <= 12);  // pipelined Q += T*M (axpy_pipe.cuh)
   static constexpr int APIPE_TS = 32;
   using APG = AxpyPipeGeom<APIPE ? N : 4, APIPE_TS>;
@@ -185,7 +194,7 @@ struct Ops {
   // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
   // outside any stream capture -- and used to size the persistent grids.
   struct Caps {
-    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0;
+    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0, dmma = 0;
   };
   // Both the shared-memory opt-ins (cudaFuncSetAttribute) and the occupancy figures are per
   // DEVICE: one slot per device ordinal, filled under a lock the first time a context of that
@@ -214,6 +223,7 @@ struct Ops {
     c.shift = occupancy_blocks(shift_update_kernel<N, kNT>, kNT, SHIFT_SMEM, sms);
     if constexpr (PIPE_OK) c.pipe = occupancy_blocks(shift_pipe_kernel<N, SHIFT_TS>, SG::NT, SG::SMEM_BYTES, sms);
     if constexpr (PAIR_OK) c.pair = occupancy_blocks(shift_pair_kernel<N, SHIFT_TS>, SG::NT, SPG::SMEM_BYTES, sms);
+    if constexpr (DMMA_OK) c.dmma = occupancy_blocks(shift_dmma_kernel<N, SHIFT_TS>, SDG::NT, SDG::SMEM_BYTES, sms);
     if constexpr (APIPE) {
       cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)APG::SMEM_BYTES);
@@ -460,6 +470,34 @@ struct Ops {
     return -static_cast<int>(cudaErrorNotSupported);
   }
 
+  static int shift_update_dmma(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
+                               const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
+                               int sms, int* launches, int paired) {
+    if constexpr (DMMA_OK) {
+      prepare(sms);
+      const int grid = clamp_grid((V + SHIFT_TS - 1) / SHIFT_TS, caps().dmma);
+      alignas(64) ShiftPairMaps maps;
+      const long long npairs = (V + 1) / 2;
+      int e = make_pair_map(&maps.Q, Q, 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
+      if (!e) e = make_pair_map(&maps.Qprev, Qprev ? Qprev : Q, 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
+      for (int s = 0; s < kMaxShifts && !e; ++s) {
+        if (fp->P[s] == nullptr || fp->X[s] == nullptr) {
+          maps.P[s] = maps.Q;  // never used: the device loop stops at the active count
+          maps.X[s] = maps.Q;
+          continue;
+        }
+        e = make_pair_map(&maps.P[s], fp->P[s], 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
+        if (!e) e = make_pair_map(&maps.X[s], fp->X[s], 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
+      }
+      if (e) return e;
+      shift_dmma_kernel<N, SHIFT_TS><<<grid, SDG::NT, SDG::SMEM_BYTES, st>>>(maps, Rm, A_odd, B_odd, A_even, B_even, V,
+                                                                             ctrl, paired);
+      if (launches) ++*launches;
+      return err();
+    }
+    return -static_cast<int>(cudaErrorNotSupported);
+  }
+
   static int shift_update_direct(cudaStream_t st, cd* Q, const ShiftPtrs* fp, const cd* Rm, const cd* A,
                                  const cd* B, long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl,
                                  int sms, int* launches) {
@@ -492,6 +530,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::shift_update,
                              &Ops<N>::shift_update_direct,
                              Ops<N>::PAIR_OK ? &Ops<N>::shift_update_pair : nullptr,
+                             Ops<N>::DMMA_OK ? &Ops<N>::shift_update_dmma : nullptr,
                              &Ops<N>::max_partials,
                              &Ops<N>::field_capacity,
                              &Ops<N>::prepare};

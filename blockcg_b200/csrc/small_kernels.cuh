@@ -987,11 +987,15 @@ scg_step_b_kernel(const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ c
     ctrl->sc_bp[s] = beta * theta * theta;
     ctrl->sc_zr[s] = zeta;
   }
-  ctrl->n_act[0] = na;  // the update kernel of this iteration serves `na` systems ...
-  ctrl->hist[na < 0 ? 0 : (na > kMaxShifts ? kMaxShifts : na)] += 1u;
-  ctrl->shift_passes += static_cast<unsigned long long>(1 + 4 * na);
-  // ... and the highest one is dropped from the next iteration on once its residual is small enough
-  if (sqrt(r2) * ctrl->sc_zeta[na - 1] < ctrl->eps_shifts) ctrl->n_unconv = na - 1;
+  // the update kernel of this iteration serves `serve` systems: x_0 and p_0 are updated outside the
+  // reference's shift loop (:65-69), i.e. always, even once the count has dropped to zero ...
+  const int serve = na > 1 ? na : 1;
+  ctrl->n_act[0] = serve;
+  ctrl->hist[serve > kMaxShifts ? kMaxShifts : serve] += 1u;
+  ctrl->shift_passes += static_cast<unsigned long long>(1 + 4 * serve);
+  // ... and the highest one is dropped from the next iteration on once its residual is small enough.  (The
+  // reference reads zeta[n_unconverged_shifts - 1] unguarded, :89: zeta[-1] once the count is zero.)
+  if (na > 0 && sqrt(r2) * ctrl->sc_zeta[na - 1] < ctrl->eps_shifts) ctrl->n_unconv = na - 1;
   const double rel = sqrt(r2) / sqrt(ctrl->sc_r2_0);
   ctrl->residual = rel;
   if (!(sqrt(r2) > ctrl->eps * sqrt(ctrl->sc_r2_0)) || ctrl->iter >= ctrl->max_it) ctrl->stop = 1;
