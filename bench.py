@@ -360,7 +360,7 @@ def run_ours(args, w, wname):
     profile = None
     for i in range(args.warmup):
         if i == args.warmup - 1 and args.profile_iters > 0:
-            ctx.set_loop_profile(args.profile_iters)  # stage-by-stage device times inside the loop (untimed step)
+            ctx.set_loop_profile(args.profile_iters, args.profile_after)  # stage-by-stage device times inside the loop (untimed step)
             step()
             profile = ctx.loop_profile()
         else:
@@ -507,7 +507,8 @@ def run_ours(args, w, wname):
         # field kernels as measured inside the loop where the window has them (stencil, Q update); the
         # multishift update per active count from the micro-benchmark, scaled by (in-loop / micro) at a = S
         inloop_upd = 0.5 * (pm["shift_odd"] + pm["shift_even"]) if pm["shift_even"] > 0 else pm["shift_odd"]
-        upd_scale = inloop_upd / t_upd[S] if t_upd[S] > 0 else 1.0
+        a_w = max(min(profile["active_systems"], S), 1)   # systems active in the profiled window
+        upd_scale = inloop_upd / t_upd[a_w] if t_upd[a_w] > 0 else 1.0
         predicted = pm["dirac_gram"] + pm["axpy_gram"] + chain_ms + upd_scale * w_ms
     loop = {"active_hist": {str(a): n for a, n in enumerate(hist) if n}, "mean_active_systems": mean_active,
             "moved_bytes_per_solve": moved, "moved_GBps": moved / loop_s / 1e9, "moved_frac_of_hbm_peak": moved / loop_s / 1e9 / peak,
@@ -520,9 +521,10 @@ def run_ours(args, w, wname):
             "microbench_ms": {"dirac_gram": kern["dirac_gram"]["ms"], "axpy_gram": kern["axpy_gram"]["ms"],
                               upd + "[a]": {str(a): t_upd[a] for a in t_upd}},
             "predicted_ms_per_iteration": predicted, "measured_ms_per_iteration": 1e3 * dev_s / max(iters, 1),
-            "prediction": "in-loop stage times of the profiled window (all systems active) with the multishift update "
-                          "re-weighted by the histogram: sum_a hist[a] * t_update(a) / iterations, t_update(a) from the "
-                          "micro-benchmark scaled by in-loop / micro-benchmark at a = S"}
+            "prediction": "stage times measured inside the loop (window of --profile-iters iterations after --profile-after, "
+                          "sustained clocks) with the multishift update re-weighted by the histogram: sum_a hist[a] * "
+                          "t_update(a) / iterations, t_update(a) from the micro-benchmark scaled by in-loop / micro-benchmark "
+                          "at the window's active count"}
     if predicted:
         loop["predicted_over_measured"] = predicted / loop["measured_ms_per_iteration"]
     roofline = {"kernel": upd + " (multishift update), histogram-weighted average launch of the timed loop",
@@ -613,6 +615,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=4, help="iterations in the bounded CPU sample")
     ap.add_argument("--profile-iters", type=int, default=64,
                     help="iterations of the last warm-up solve timed stage by stage inside the loop (0: off)")
+    ap.add_argument("--profile-after", type=int, default=3000,
+                    help="iterations to run before the profiled window starts (sustained clocks)")
     ap.add_argument("--multi-lockstep-iters", type=int, default=200,
                     help="N > 1 GPUs: iterations of the slab loop compared with the single-domain loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")

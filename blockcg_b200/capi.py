@@ -48,6 +48,11 @@ class SolveStats(C.Structure):
                 ("resid_shift", C.c_double * MAX_SHIFTS)]
 
 
+class LoopProfile(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("first_iteration", C.c_int), ("active_systems", C.c_int),
+                ("ms", C.c_double * 8)]
+
+
 class BcgError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("%s: %s" % (STATUS.get(code, code), msg))
@@ -114,8 +119,8 @@ def load():
     lib.bcg_solve_scg.argtypes = [C.c_void_p, C.POINTER(_dp), _dp, _dp, C.c_int, C.c_double, C.c_double,
                                   C.c_int, C.POINTER(SolveInfo)]
     lib.bcg_last_solve_stats.argtypes = [C.c_void_p, C.POINTER(SolveStats)]
-    lib.bcg_set_loop_profile.argtypes = [C.c_void_p, C.c_int]
-    lib.bcg_get_loop_profile.argtypes = [C.c_void_p, _dp, _ip]
+    lib.bcg_set_loop_profile.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.bcg_get_loop_profile.argtypes = [C.c_void_p, C.POINTER(LoopProfile)]
     lib.bcg_small_inverse.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _ip]
     lib.bcg_small_lu_solve.argtypes = [C.c_void_p, _dp, _dp, _dp]
     lib.bcg_bench_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp,
@@ -348,16 +353,17 @@ class Context:
                 "active_hist": list(st.active_hist), "shift_update_field_passes": int(st.shift_update_field_passes),
                 "resid_shift": list(st.resid_shift)[:max(st.n_shifts, 1)]}
 
-    def set_loop_profile(self, n_iterations):
-        """Time the first n_iterations of the next solve stage by stage (CUDA events inside the loop)."""
-        self._ck(self.lib.bcg_set_loop_profile(self._h, int(n_iterations)))
+    def set_loop_profile(self, n_iterations, after_iterations=0):
+        """Time n_iterations of the next solve stage by stage (CUDA events inside the loop), starting once
+        after_iterations have run."""
+        self._ck(self.lib.bcg_set_loop_profile(self._h, int(n_iterations), int(after_iterations)))
 
     def loop_profile(self):
-        ms = (C.c_double * 8)()
-        n = C.c_int(0)
-        self._ck(self.lib.bcg_get_loop_profile(self._h, ms, C.byref(n)))
+        lp = LoopProfile()
+        self._ck(self.lib.bcg_get_loop_profile(self._h, C.byref(lp)))
         keys = ["dirac_gram", "step_a", "axpy_gram", "step_b", "shift_odd", "shift_even", "halo", "iteration"]
-        return {"iterations": n.value, "ms": dict(zip(keys, [float(v) for v in ms]))}
+        return {"iterations": lp.iterations, "first_iteration": lp.first_iteration, "active_systems": lp.active_systems,
+                "ms": dict(zip(keys, [float(v) for v in lp.ms]))}
 
     # ---- the device N x N routines in isolation (unit tests) ----
     def small_inverse(self, A, pivot=True):

@@ -147,7 +147,7 @@ struct bcg_ctx {
   GraphCache graph;
   // in-loop profile (bcg_set_loop_profile): the first `prof_want` iterations of the next solve are enqueued
   // kernel by kernel with an event after each, instead of as a graph batch
-  int prof_want = 0, prof_n = 0;
+  int prof_want = 0, prof_after = 0, prof_n = 0, prof_first = 0, prof_active = 0;
   std::vector<cudaEvent_t> prof_ev;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::string err;
@@ -1015,51 +1015,57 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     g.launches = launches;
     g.key = key;
   }
-  // optional in-loop profile: the first iterations one kernel at a time with an event after each stage
-  // (same kernels, same stream, same control flow on the device; only the submission differs)
-  c->prof_n = 0;
-  if (c->prof_want > 0) {
-    const int P = c->prof_want;
-    while (static_cast<int>(c->prof_ev.size()) < 7 * P) {
-      cudaEvent_t e;
-      CU(cudaEventCreate(&e));
-      c->prof_ev.push_back(e);
-    }
-    int l = 0;
-    for (int i = 0; i < P; ++i) {
-      int r = enqueue_iteration(c, p, &l, c->prof_ev.data() + 7 * i);
-      if (r) return r;
-    }
-    *launches_total += l;
-    CU(cudaMemcpyAsync(c->ctrl_host, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    const int ran = c->ctrl_host[0].iter < P ? c->ctrl_host[0].iter : P;  // a solve shorter than the window
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int n_odd = 0, n_even = 0;
-    for (int i = 0; i < ran; ++i) {
-      const cudaEvent_t* ev = c->prof_ev.data() + 7 * i;
-      float ms[6];
-      for (int k = 0; k < 6; ++k) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
-      const bool odd = ((i + 1) & 1) != 0;  // iteration number i + 1
-      acc[0] += ms[0];
-      acc[1] += ms[1];
-      acc[2] += ms[2];
-      acc[3] += ms[3];
-      acc[odd ? 4 : 5] += ms[4];
-      acc[6] += ms[5];
-      (odd ? n_odd : n_even) += 1;
-      for (int k = 0; k < 6; ++k) acc[7] += ms[k];
-    }
-    for (int k = 0; k < 8; ++k) c->prof_ms[k] = ran ? acc[k] / ran : 0.0;
-    c->prof_ms[4] = n_odd ? acc[4] / n_odd : 0.0;   // per odd / per even iteration
-    c->prof_ms[5] = n_even ? acc[5] / n_even : 0.0;
-    c->prof_n = ran;
-    c->prof_want = 0;  // one solve
-  }
   // pipelined submission: look at batch i-1's mirror after submitting batch i
   int submitted = 0;
   bool done = false;
+  c->prof_n = 0;
   while (!done) {
+    if (c->prof_want > 0 && submitted * batch >= c->prof_after) {
+      // in-loop profile: the next iterations one kernel at a time with an event after each stage (same
+      // kernels, same stream, same control flow on the device; only the submission differs)
+      const int P = c->prof_want;
+      c->prof_want = 0;  // one window, one solve
+      while (static_cast<int>(c->prof_ev.size()) < 7 * P) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+      }
+      CU(cudaMemcpyAsync(c->ctrl_host, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      const int first = c->ctrl_host[0].iter;
+      int l = 0;
+      for (int i = 0; i < P; ++i) {
+        int r = enqueue_iteration(c, p, &l, c->prof_ev.data() + 7 * i);
+        if (r) return r;
+      }
+      *launches_total += l;
+      CU(cudaMemcpyAsync(c->ctrl_host, c->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      int ran = c->ctrl_host[0].iter - first;  // the solve may end inside the window
+      if (ran > P) ran = P;
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int n_odd = 0, n_even = 0;
+      for (int i = 0; i < ran; ++i) {
+        const cudaEvent_t* ev = c->prof_ev.data() + 7 * i;
+        float ms[6];
+        for (int k = 0; k < 6; ++k) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+        const bool odd = ((first + i + 1) & 1) != 0;  // iteration number first + i + 1
+        acc[0] += ms[0];
+        acc[1] += ms[1];
+        acc[2] += ms[2];
+        acc[3] += ms[3];
+        acc[odd ? 4 : 5] += ms[4];
+        acc[6] += ms[5];
+        (odd ? n_odd : n_even) += 1;
+        for (int k = 0; k < 6; ++k) acc[7] += ms[k];
+      }
+      for (int k = 0; k < 8; ++k) c->prof_ms[k] = ran > 0 ? acc[k] / ran : 0.0;
+      c->prof_ms[4] = n_odd ? acc[4] / n_odd : 0.0;   // per odd / per even iteration
+      c->prof_ms[5] = n_even ? acc[5] / n_even : 0.0;
+      c->prof_n = ran > 0 ? ran : 0;
+      c->prof_first = first;
+      c->prof_active = c->ctrl_host[0].n_unconv;
+    }
     CU(cudaGraphLaunch(g.exec, c->stream));
     *launches_total += g.launches;
     const int slot = submitted & 1;
@@ -1424,15 +1430,18 @@ int bcg_last_solve_stats(bcg_ctx* c, bcg_solve_stats* out) {
   return BCG_OK;
 }
 
-int bcg_set_loop_profile(bcg_ctx* c, int n_iterations) {
-  if (!c || n_iterations < 0 || n_iterations > 4096) return fail(c, BCG_ERR_INVALID, "bad profile window");
+int bcg_set_loop_profile(bcg_ctx* c, int n_iterations, int after_iterations) {
+  if (!c || n_iterations < 0 || n_iterations > 4096 || after_iterations < 0) return fail(c, BCG_ERR_INVALID, "bad profile window");
   c->prof_want = n_iterations;
+  c->prof_after = after_iterations;
   return BCG_OK;
 }
-int bcg_get_loop_profile(bcg_ctx* c, double* ms_out, int* n_out) {
-  if (!c || !ms_out || !n_out) return fail(c, BCG_ERR_INVALID, "null argument");
-  for (int k = 0; k < 8; ++k) ms_out[k] = c->prof_ms[k];
-  *n_out = c->prof_n;
+int bcg_get_loop_profile(bcg_ctx* c, bcg_loop_profile* out) {
+  if (!c || !out) return fail(c, BCG_ERR_INVALID, "null argument");
+  for (int k = 0; k < 8; ++k) out->ms[k] = c->prof_ms[k];
+  out->iterations = c->prof_n;
+  out->first_iteration = c->prof_first;
+  out->active_systems = c->prof_active;
   return BCG_OK;
 }
 

@@ -189,14 +189,20 @@ typedef struct {
 } bcg_solve_stats;
 int bcg_last_solve_stats(bcg_ctx* ctx, bcg_solve_stats* out);
 
-/* In-loop profile: the first n_iterations (<= 4096) of the NEXT solve on this context are submitted
- * kernel by kernel with a CUDA event after each stage instead of as graph batches; the solve is otherwise
- * unchanged.  bcg_get_loop_profile returns mean device milliseconds per iteration over the window:
- * ms_out[0] stencil + fused Gram, [1] coefficient A-step, [2] Q update + fused Gram, [3] coefficient B-step,
- * [4] multishift update of an ODD iteration, [5] of an EVEN iteration (paired update: shift_pair.cuh),
- * [6] halo refresh, [7] whole iteration; *n_out = iterations in the window (0: no profile taken). */
-int bcg_set_loop_profile(bcg_ctx* ctx, int n_iterations);
-int bcg_get_loop_profile(bcg_ctx* ctx, double* ms_out /* [8] */, int* n_out);
+/* In-loop profile: n_iterations (<= 4096) of the NEXT solve on this context, starting once at least
+ * after_iterations have run (so the GPU is at its sustained clocks), are submitted kernel by kernel with a
+ * CUDA event after each stage instead of as graph batches; the solve is otherwise unchanged.  ms[] = mean
+ * device milliseconds per iteration over the window: [0] stencil + fused Gram, [1] coefficient A-step,
+ * [2] Q update + fused Gram, [3] coefficient B-step, [4] multishift update of an ODD iteration, [5] of an
+ * EVEN iteration (paired update: shift_pair.cuh), [6] halo refresh, [7] whole iteration. */
+typedef struct {
+  int iterations;       /* iterations in the window (0: no profile taken) */
+  int first_iteration;  /* iterations completed before the window          */
+  int active_systems;   /* systems still being updated at the end of it    */
+  double ms[8];
+} bcg_loop_profile;
+int bcg_set_loop_profile(bcg_ctx* ctx, int n_iterations, int after_iterations);
+int bcg_get_loop_profile(bcg_ctx* ctx, bcg_loop_profile* out);
 
 /* ---- unit-test entry points of the device N x N routines (isolated parity with Eigen) ----------
  * bcg_small_inverse : out = a^-1 with the Gauss-Jordan inverse the (S)BCGrQ loops use in place of

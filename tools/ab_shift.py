@@ -42,9 +42,9 @@ for var in variants:
         for h in hs[1 + S:]:
             ctx.free(h)
         xs = hs[1:1 + S]
-        ctx.set_loop_profile(64)
+        ctx.set_loop_profile(64, 200)
         info = ctx.solve_sbcgrq_dev(xs, hb, shifts, 1e-10, 1e-15, max_it)
-        out["profile"] = ctx.loop_profile()["ms"]
+        out["profile"] = ctx.loop_profile()
         info = ctx.solve_sbcgrq_dev(xs, hb, shifts, 1e-10, 1e-15, max_it)
         out["solve_ms"] = info.solve_ms
         out["ms_per_iteration"] = info.solve_ms / max(info.iterations, 1)

@@ -15,5 +15,5 @@ with blockcg_b200.Context(V, N, max_shifts=S) as ctx:
         ctx.copy(h, hs[0])
     for w in sys.argv[4:]:
         w = int(w)
-        nh, ns = (1 + 2 * S, S) if w in (4, 7, 8) else (2, 1)
+        nh, ns = (1 + 2 * S, S) if w in (4, 7, 8, 13) else (2, 1)
         print(w, ctx.bench_kernel(w, 2, hs[:nh], ns))
