@@ -118,7 +118,7 @@ def test_benchmark_default_config(bcg, oracle):
     assert it <= int(g["it_sbcgrq"]) + 1
 
 
-@pytest.mark.parametrize("V,N", [(4096, 12), (5000, 8), (777, 4), (6000, 1), (1500, 16), (2049, 3)])
+@pytest.mark.parametrize("V,N", [(4096, 12), (5000, 8), (777, 4), (6000, 1), (1500, 16), (2049, 3), (1100, 32)])
 def test_primitives_vs_oracle_larger(bcg, oracle, V, N):
     """Multi-tile / multi-CTA sizes (ragged last tile) against the oracle."""
     rng = np.random.default_rng(V + N)
@@ -545,3 +545,29 @@ def test_headline_volume_lockstep_vs_reference(bcg, oracle):
         ha = ctx.field()
         G = ctx.op(ha, hb, want_gram=True)
         assert np.abs(G - G.conj().T).max() / np.abs(G).max() < 1e-13 and np.all(G.diagonal().real > 0)
+
+
+@pytest.mark.parametrize("V,N", [(700, 16), (333, 32), (2000, 8)])
+def test_solvers_other_block_sizes_vs_oracle(bcg, oracle, V, N):
+    """N_rhs = 8, 16 (tensor-instruction update) and 32 (configs[4] names N up to 32; first-generation
+    kernels): BCGrQ, SBCGrQ and BCG against the oracle run with a tree-shaped Gram -- iterations within 1 %,
+    solutions <= 1e-9, true residual < 2 eps (test/solvers.cpp:116)."""
+    mass, eps = 0.2, 1e-10
+    shifts = [0.0, 1e-3, 0.05, 0.4]
+    U, B = oracle.make_inputs(V, N, 8)
+    D = bcg.dirac_op(V, mass, links=U)
+    X = np.empty_like(B)
+    it = bcg.BCGrQ(X, B, D, eps)
+    Xo, ito, _ = oracle.BCGrQ(U, B, mass, eps, chunk=32)
+    assert abs(it - ito) <= max(1, ito // 100) and rel(X, Xo) < 1e-9
+    Xs = [np.empty_like(B) for _ in shifts]
+    it = bcg.SBCGrQ(Xs, B, D, shifts, eps, 1e-15)
+    Xso, itso, _, _ = oracle.SBCGrQ(U, B, mass, shifts, eps, 1e-15, chunk=32)
+    assert abs(it - itso) <= max(1, itso // 100)
+    for s, sig in enumerate(shifts):
+        assert rel(Xs[s], Xso[s]) < 1e-9
+        assert oracle.true_residual(U, B, Xs[s], mass, sig).max() < 2 * eps
+    assert np.array_equal(Xs[0], X)   # SBCGrQ shift 0 == BCGrQ, bit for bit (SURVEY 3.2)
+    it = bcg.BCG(X, B, D, eps)
+    Xb, itb, _ = oracle.BCG(U, B, mass, eps, chunk=32)
+    assert abs(it - itb) <= max(2, itb // 50) and rel(X, Xb) < 1e-8
