@@ -30,7 +30,7 @@ EXPORTS = [
     "bcg_add", "bcg_add_scalar", "bcg_rescale_add", "bcg_trsm", "bcg_thinqr", "bcg_true_residual",
     "bcg_solve_bcg_dev", "bcg_solve_bcgrq_dev", "bcg_solve_sbcgrq_dev", "bcg_solve_bcg", "bcg_solve_bcgrq",
     "bcg_solve_sbcgrq", "bcg_bench_kernel", "bcg_solve_cg_dev", "bcg_solve_scg_dev", "bcg_solve_cg", "bcg_solve_scg",
-    "bcg_last_solve_stats", "bcg_small_inverse", "bcg_small_lu_solve", "bcg_set_loop_profile", "bcg_get_loop_profile",
+    "bcg_last_solve_stats", "bcg_small_inverse", "bcg_small_lu_solve", "bcg_set_loop_profile", "bcg_get_loop_profile", "bcg_shift_schedule",
 ]
 
 
@@ -121,6 +121,7 @@ def load():
     lib.bcg_last_solve_stats.argtypes = [C.c_void_p, C.POINTER(SolveStats)]
     lib.bcg_set_loop_profile.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bcg_get_loop_profile.argtypes = [C.c_void_p, C.POINTER(LoopProfile)]
+    lib.bcg_shift_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip]
     lib.bcg_small_inverse.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _ip]
     lib.bcg_small_lu_solve.argtypes = [C.c_void_p, _dp, _dp, _dp]
     lib.bcg_bench_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp,
@@ -140,6 +141,15 @@ def mat_to_cm(M):
 
 def mat_from_cm(buf, N):
     return np.ascontiguousarray(buf.reshape(N, N).T)
+
+
+def shift_schedule(schedule, iteration, stop, n_active, n_active_prev):
+    """Items of one launch of the multishift update: [(kind, system)], field passes (host-side, no device)."""
+    lib = load()
+    kinds, systems = (C.c_int * (MAX_SHIFTS + 2))(), (C.c_int * (MAX_SHIFTS + 2))()
+    passes = C.c_int(0)
+    n = lib.bcg_shift_schedule(schedule, iteration, 1 if stop else 0, n_active, n_active_prev, kinds, systems, C.byref(passes))
+    return [(kinds[i], systems[i]) for i in range(n)], passes.value
 
 
 class Context:

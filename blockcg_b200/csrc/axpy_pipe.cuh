@@ -43,7 +43,8 @@ struct AxpyPipeGeom {
 
 template <int N, int TS, bool GRAM>
 __global__ void __launch_bounds__(AxpyPipeGeom<N, TS>::NT, 1)
-axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT,
+axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQout,
+                 const __grid_constant__ CUtensorMap tmT,
                  const cd* __restrict__ M, long long V, cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl,
                  const GramPeers peers, int reverse) {
   // reverse != 0: tiles are visited from the high end of the field down.  The stencil that ran
@@ -108,7 +109,7 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < nmine; ++i) {
       const int st = i % NS;
       mbar_wait(cdone + st, static_cast<uint32_t>((i / NS) & 1));
-      tma_store_2d(&tmQ, 0, tile_pair0(i), sbuf + st * STAGE + TILE);
+      tma_store_2d(&tmQout, 0, tile_pair0(i), sbuf + st * STAGE + TILE);  // in place, or into the other Q field (staggered schedule)
       bulk_commit();
       bulk_wait_read0();
       mbar_arrive(sdone + st);

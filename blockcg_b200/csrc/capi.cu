@@ -764,7 +764,7 @@ int bcg_add(bcg_ctx* c, int dst, int src, const double* m_host) {
   int r = upload_mat(c, M_SCRATCH, m_host, 0);
   if (r) return r;
   KL(c->ops->axpy_gram(c->stream, fptr(c, dst), fptr(c, src), mat(c, M_SCRATCH), c->V, nullptr, nullptr, c->sms,
-                       nullptr, nullptr));
+                       nullptr, nullptr, nullptr));
   CU(cudaStreamSynchronize(c->stream));
   return BCG_OK;
 }
@@ -852,10 +852,11 @@ int bcg_true_residual(bcg_ctx* c, int x, int b, double sigma, double* res_host) 
 // ---- the iteration loops ---------------------------------------------------------------------
 namespace {
 
-// Shifted systems served every second iteration (shift_pair.cuh).  BCG_PAIR=0 / 1 overrides.
-bool pair_default() {  // read per solve, so that a test can compare both paths in one process
+// Schedule of the multishift update (build_shift_items in common.cuh): BCG_PAIR = 0 plain, 1 alternating,
+// 2 staggered (default where the kernels support it).
+int pair_default() {  // read per solve, so that a test can compare the schedules in one process
   const char* e = std::getenv("BCG_PAIR");
-  return e ? std::atoi(e) != 0 : true;
+  return e ? std::atoi(e) : 2;
 }
 
 // The (S)BCGrQ update on the FP64 tensor instruction (shift_dmma.cuh).  BCG_DMMA=0 selects the DFMA kernels.
@@ -867,7 +868,8 @@ bool dmma_default() {  // read per solve, so that a test can compare both paths 
 struct LoopPlan {
   int kind;  // 0 BCG, 1 (S)BCGrQ, 2 CG / SCG (scalar coefficients, N_rhs = 1)
   int n_shifts;
-  bool pair;  // multishift loop with the paired update
+  int pair;   // schedule of the multishift update: 0 plain, 1 alternating, 2 staggered (build_shift_items)
+  cd* Qbuf[2];  // staggered schedule: the two Q fields ([0] holds Q of even iteration numbers, incl. the initial one)
   bool dmma;  // (S)BCGrQ update by shift_dmma_kernel (plain or paired schedule)
   cd* P0;
   cd* T;
@@ -879,7 +881,8 @@ struct LoopPlan {
 // enqueue one iteration on c->stream
 // marks (optional): 7 events, recorded before the stencil and after each of the six stages
 // (stencil+Gram, A-step, Q update+Gram, B-step, multishift update, halo)
-int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t* marks = nullptr) {
+// pos: iterations completed before this one (its parity selects the Q field of the staggered schedule)
+int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t* marks = nullptr, int pos = 0) {
 #define BCG_MARK(i) do { if (marks) CU(cudaEventRecord(marks[i], c->stream)); } while (0)
   BCG_MARK(0);
   const cd* gsrc;
@@ -903,7 +906,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
     ++*launches;
     CU(cudaGetLastError());
     BCG_MARK(2);
-    np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches, nullptr);
+    np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches, nullptr, nullptr);
     KL(np);
     r = gram_finalize(c, np, &gsrc, &nsrc, launches, false);
     if (r) return r;
@@ -937,8 +940,12 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   ++*launches;
   CU(cudaGetLastError());
   BCG_MARK(2);
-  np = c->ops->axpy_gram(c->stream, p.Q, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches,
-                         fused ? &gp1 : nullptr);
+  // staggered schedule: Q ping-pongs between two fields -- Q_pos (the previous iteration's, kept intact for the
+  // deferred updates) is read, the new Q is written into the other one and normalised there by the update kernel
+  cd* Qin = (p.pair == 2) ? p.Qbuf[pos & 1] : p.Q;
+  cd* Qout = (p.pair == 2) ? p.Qbuf[(pos + 1) & 1] : p.Q;
+  np = c->ops->axpy_gram(c->stream, Qin, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches,
+                         fused ? &gp1 : nullptr, Qout);
   KL(np);
   r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
@@ -953,9 +960,9 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   CU(cudaGetLastError());
   BCG_MARK(4);
   if (p.dmma)
-    KL(c->ops->shift_update_dmma(c->stream, p.Q, p.pair ? fptr(c, c->work_Qp) : nullptr, &p.fp, mat(c, M_RHO_CUR),
-                                 c->mats + c->L.A(0, 1), c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0),
-                                 c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair ? 1 : 0));
+    KL(c->ops->shift_update_dmma(c->stream, Qout, p.pair == 2 ? Qin : (p.pair == 1 ? fptr(c, c->work_Qp) : nullptr), &p.fp,
+                                 mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1), c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0),
+                                 c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair));
   else if (p.pair)
     KL(c->ops->shift_update_pair(c->stream, p.Q, fptr(c, c->work_Qp), &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1),
                                  c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0), c->mats + c->L.B(0, 0), c->V, c->ctrl,
@@ -972,7 +979,8 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
 }
 
 int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launches_total) {
-  const int batch = pick_batch(c, p.n_shifts);
+  int batch = pick_batch(c, p.n_shifts);
+  batch += batch & 1;  // even: an iteration's position in the batch then has the parity of its number (staggered schedule)
   // (re)build the graph of `batch` iterations if anything it bakes in changed
   std::vector<const void*> key = {p.P0, p.T, p.Q};
   for (int s = 0; s < p.n_shifts; ++s) {
@@ -988,6 +996,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     key.push_back(bits);
   }
   key.push_back(p.pair ? &c->work_Qp : nullptr);
+  key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(p.pair)));
   key.push_back(p.dmma ? &c->work_Q : nullptr);
   GraphCache& g = c->graph;
   if (!g.exec || g.kind != p.kind || g.n_shifts != p.n_shifts || g.batch != batch || g.key != key) {
@@ -999,7 +1008,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int r = BCG_OK;
-    for (int i = 0; i < batch && r == BCG_OK; ++i) r = enqueue_iteration(c, p, &launches);
+    for (int i = 0; i < batch && r == BCG_OK; ++i) r = enqueue_iteration(c, p, &launches, nullptr, i);
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     if (r != BCG_OK) {
       if (graph) cudaGraphDestroy(graph);
@@ -1035,7 +1044,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
       const int first = c->ctrl_host[0].iter;
       int l = 0;
       for (int i = 0; i < P; ++i) {
-        int r = enqueue_iteration(c, p, &l, c->prof_ev.data() + 7 * i);
+        int r = enqueue_iteration(c, p, &l, c->prof_ev.data() + 7 * i, first + i);
         if (r) return r;
       }
       *launches_total += l;
@@ -1140,9 +1149,12 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   if (r) return r;
   r = init_ctrl(c, n_shifts, sigma, eps, eps_shifts, max_it);
   if (r) return r;
-  const bool pair = pair_default() && n_shifts > 1 && c->work_Qp >= 0 &&
-                    (c->ops->shift_update_pair != nullptr || (dmma_default() && c->ops->shift_update_dmma != nullptr));
-  c->L.pair = pair ? 1 : 0;
+  const bool dmma = dmma_default() && c->ops->shift_update_dmma != nullptr;
+  int pair = (n_shifts > 1 && c->work_Qp >= 0) ? pair_default() : 0;
+  if (pair == 2 && !(dmma && c->ops->out_of_place_axpy)) pair = 1;  // staggering needs the tensor-instruction kernel and Q ping-pong
+  if (pair == 1 && !(dmma || c->ops->shift_update_pair != nullptr)) pair = 0;
+  if (pair < 0 || pair > 2) pair = 0;
+  c->L.pair = pair;
   int64_t launches = 0;
   int l = 0;
   CU(cudaEventRecord(c->ev[0], c->stream));
@@ -1165,7 +1177,9 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   std::memset(&p, 0, sizeof p);
   p.kind = 1;
   p.pair = pair;
-  p.dmma = dmma_default() && c->ops->shift_update_dmma != nullptr;
+  p.dmma = dmma;
+  p.Qbuf[0] = Q;
+  p.Qbuf[1] = (pair == 2) ? fptr(c, c->work_Qp) : Q;
   p.n_shifts = n_shifts;
   p.T = fptr(c, c->work_T);
   p.Q = Q;
@@ -1430,6 +1444,22 @@ int bcg_last_solve_stats(bcg_ctx* c, bcg_solve_stats* out) {
   return BCG_OK;
 }
 
+// Host-side view of the update schedule the kernels follow (no device needed): the items one launch works
+// through.  kinds[i]: 0 Q, 1 Q kept, 2 previous Q, 3 / 4 / 5 system systems[i] gets this iteration's / the
+// previous iteration's / both updates.  Returns the number of items (<= BCG_MAX_SHIFTS + 2).
+int bcg_shift_schedule(int schedule, int iteration, int stop, int n_active, int n_active_prev, int* kinds, int* systems,
+                       int* field_passes) {
+  ShiftItem items[kMaxShiftItems];
+  int passes = 0;
+  const int n = build_shift_items(schedule, iteration, stop, n_active, n_active_prev, items, &passes);
+  for (int i = 0; i < n; ++i) {
+    if (kinds) kinds[i] = items[i].kind;
+    if (systems) systems[i] = items[i].s;
+  }
+  if (field_passes) *field_passes = passes;
+  return n;
+}
+
 int bcg_set_loop_profile(bcg_ctx* c, int n_iterations, int after_iterations) {
   if (!c || n_iterations < 0 || n_iterations > 4096 || after_iterations < 0) return fail(c, BCG_ERR_INVALID, "bad profile window");
   c->prof_want = n_iterations;
@@ -1508,6 +1538,10 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   MatLayout Lp = c->L;
   Lp.pair = 1;
   const bool use_dmma = dmma_default() && c->ops->shift_update_dmma != nullptr && (which == 13 || which == 4);
+  // schedule the paired micro-benchmark runs (as solve_rq picks it)
+  int bench_sched = pair_default();
+  if (bench_sched == 2 && !(use_dmma && c->ops->out_of_place_axpy)) bench_sched = 1;
+  if (bench_sched < 1 || bench_sched > 2) bench_sched = 1;
   if (which == 13 || (which == 4 && use_dmma)) {  // paired multishift update: one repetition = an odd and an even iteration's launch
     if (!c->ops->shift_update_pair && !use_dmma) return fail(c, BCG_ERR_INVALID, "no paired multishift kernel at N=%d", c->N);
     if (c->work_Qp < 0) {
@@ -1518,10 +1552,10 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
     Ctrl hc[2];
     std::memset(hc, 0, sizeof hc);
     for (int i = 0; i < 2; ++i) {
-      hc[i].iter = 1 + i;
+      hc[i].iter = (bench_sched == 2 ? 2 : 1) + i;  // staggered: two steady-state iterations; alternating: an odd + even pair
       hc[i].n_unconv = n_shifts;
       hc[i].n_shifts = n_shifts;
-      hc[i].n_act[1] = n_shifts;
+      hc[i].n_act[0] = hc[i].n_act[1] = n_shifts;
     }
     CU(cudaMemcpy(c->bench_ctrl, hc, sizeof hc, cudaMemcpyHostToDevice));
   }
@@ -1532,7 +1566,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
           if (use_dmma)
             KL(c->ops->shift_update_dmma(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
                                          c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
-                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l, 1));
+                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l, bench_sched));
           else
             KL(c->ops->shift_update_pair(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
                                          c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
@@ -1570,7 +1604,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         break;
       case 3:
         KL(c->ops->axpy_gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, c->gpart, nullptr,
-                             c->sms, l, nullptr));
+                             c->sms, l, nullptr, nullptr));
         break;
       case 4:
         if (use_dmma) {  // every system every iteration, on the tensor-instruction kernel
@@ -1592,7 +1626,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         break;
       case 5:
         KL(c->ops->axpy_gram(c->stream, fptr(c, h[0]), fptr(c, h[1]), mat(c, M_SCRATCH), c->V, nullptr, nullptr,
-                             c->sms, l, nullptr));
+                             c->sms, l, nullptr, nullptr));
         break;
       case 6:
         KL(c->ops->rescale_add(c->stream, fptr(c, h[0]), mat(c, M_SCRATCH), fptr(c, h[1]), 1.0, c->V, c->sms, l));

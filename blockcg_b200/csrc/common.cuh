@@ -97,28 +97,88 @@ struct Ctrl {
 };
 
 // What one launch of the multishift update does, as a function of the control block the B-step of
-// the same iteration has left behind.  mode 0: plain (Q, then every active system); 1: first of a
-// pair (Q kept as Qprev, system 0 only); 2: second of a pair (Q, Qprev, system 0, both updates of
-// the shifted systems).  Shared by the kernel (shift_pair.cuh) and by the B-step's byte accounting.
-struct ShiftLaunchPlan {
-  int mode, n1, n2;
-  // field-sized passes through HBM (reads + writes)
-  __host__ __device__ int passes() const {
-    if (mode == 1) return 3 + 4;                 // Q in, Q out, Qprev out ; X_0, P_0 in and out
-    if (mode == 2) return 3 + 4 + 4 * (n1 - 1);  // Q in, Q out, Qprev in ; system 0 ; shifted systems once for both updates
-    return 2 + 4 * n2;
-  }
+// the same iteration has left behind: the list of ITEMS a tile goes through.  Shared by the kernels
+// (shift_pair.cuh, shift_dmma.cuh) and by the B-step's byte accounting.
+//   schedule 0  plain      : every active system is updated in every iteration.
+//   schedule 1  alternating: the shifted systems (s >= 1) never feed back into the main recurrence, so
+//                            their two updates of an odd + even iteration pair are applied together in the
+//                            even one, from the Q of both iterations (the odd one's is kept in a second field).
+//   schedule 2  staggered  : the same deferral, but odd-numbered systems are served in odd iterations and
+//                            even-numbered ones in even iterations, so every launch carries the same load
+//                            (FP64 work and HBM traffic balanced launch by launch); Q ping-pongs between two
+//                            fields (Q -= T alpha writes into the other one), so the previous Q is kept for free.
+// A system that retired between the two iterations gets the earlier update only; the iteration the
+// loop ends on (`stop`) brings every system up to date.
+enum : int { KQ = 0, KQ_KEEP = 1, KQPREV = 2, KCUR = 3, KPREV = 4, KBOTH = 5 };
+struct ShiftItem {
+  signed char kind;  // KQ: Q <- Q rho^-1 ; KQ_KEEP: ... and kept as Qprev ; KQPREV: previous Q (read only) ;
+  signed char s;     // KCUR / KPREV / KBOTH: system s gets this iteration's / the previous one's / both updates
 };
-__host__ __device__ inline ShiftLaunchPlan shift_launch_plan(bool paired, int iter, int stop, int n_unconv, int n_act_odd) {
-  ShiftLaunchPlan p;
+constexpr int kMaxShiftItems = kMaxShifts + 2;
+// n_now: systems active in this iteration; n_prev: in the previous one (n_act[(iter - 1) & 1]).
+// Returns the number of items; *passes = field-sized passes through HBM (reads + writes).
+__host__ __device__ inline int build_shift_items(int schedule, int iter, int stop, int n_now, int n_prev,
+                                                 ShiftItem* out, int* passes) {
+  int n = 0, systems = 0, qpasses = 2;  // Q in, Q out
   const bool odd = (iter & 1) != 0;
-  p.n2 = n_unconv;
-  p.n1 = odd ? n_unconv : n_act_odd;  // systems active in the odd iteration of this pair
-  // nothing is deferred when the loop ends on this iteration or no shifted system is active any more
-  if (paired && odd && !stop && p.n1 > 1) p.mode = 1;
-  else if (paired && !odd && p.n1 > 1) p.mode = 2;
-  else p.mode = 0;
-  return p;
+#define BCG_ADD_ITEM(k_, s_)                        \
+  do {                                              \
+    if (out) {                                      \
+      out[n].kind = static_cast<signed char>(k_);   \
+      out[n].s = static_cast<signed char>(s_);      \
+    }                                               \
+    ++n;                                            \
+  } while (0)
+  if (schedule == 1) {
+    const int n1 = odd ? n_now : n_prev;  // systems active in the odd iteration of this pair
+    if (odd && !stop && n1 > 1) {         // first of a pair: nothing is deferred when the loop ends here
+      BCG_ADD_ITEM(KQ_KEEP, -1);
+      BCG_ADD_ITEM(KCUR, 0);
+      qpasses = 3;
+      systems = 1;
+    } else if (!odd && n1 > 1) {          // second of a pair
+      BCG_ADD_ITEM(KQ, -1);
+      BCG_ADD_ITEM(KQPREV, -1);
+      BCG_ADD_ITEM(KCUR, 0);
+      for (int s = 1; s < n1; ++s) BCG_ADD_ITEM(s < n_now ? KBOTH : KPREV, s);
+      qpasses = 3;
+      systems = n1;
+    } else {
+      BCG_ADD_ITEM(KQ, -1);
+      for (int s = 0; s < n_now; ++s) BCG_ADD_ITEM(KCUR, s);
+      systems = n_now;
+    }
+  } else if (schedule == 2) {
+    const int np = (iter >= 2) ? n_prev : 0;  // the first iteration has no predecessor
+    BCG_ADD_ITEM(KQ, -1);
+    bool need_prev = false;
+    for (int s = 1; s < np; ++s)
+      if ((s & 1) == (iter & 1)) need_prev = true;
+    if (need_prev) {
+      BCG_ADD_ITEM(KQPREV, -1);
+      qpasses = 3;
+    }
+    BCG_ADD_ITEM(KCUR, 0);
+    systems = 1;
+    const int top = np > n_now ? np : n_now;
+    for (int s = 1; s < top; ++s) {
+      const bool mine = (s & 1) == (iter & 1), ap = s < np, ac = s < n_now;
+      if (mine && (ap || ac)) {
+        BCG_ADD_ITEM(ap && ac ? KBOTH : (ap ? KPREV : KCUR), s);
+        ++systems;
+      } else if (!mine && stop && ac) {  // the loop ends here: this iteration's update of the other group is not deferred
+        BCG_ADD_ITEM(KCUR, s);
+        ++systems;
+      }
+    }
+  } else {
+    BCG_ADD_ITEM(KQ, -1);
+    for (int s = 0; s < n_now; ++s) BCG_ADD_ITEM(KCUR, s);
+    systems = n_now;
+  }
+#undef BCG_ADD_ITEM
+  if (passes) *passes = qpasses + 4 * systems;
+  return n;
 }
 
 // ---- peer-memory exchange between the ranks of a slab decomposition (NVLink P2P) -------------

@@ -33,8 +33,11 @@ struct OpsTable {
                       int* launches);
   int (*gram)(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
               int* launches);
+  // Q += T*M (+ Gram of the result); Qout != nullptr: the result goes to Qout, Q is left untouched
+  // (only where out_of_place_axpy is set)
   int (*axpy_gram)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
-                   const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers);
+                   const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers, cd* Qout);
+  int out_of_place_axpy;
   int fused_exchange;  // 1 if dirac / axpy_gram push the final Gram block to the peers themselves
   int (*axpy_gram_v1)(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
                       const Ctrl* ctrl, int sms, int* launches);
@@ -54,10 +57,11 @@ struct OpsTable {
                            const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
                            int sms, int* launches);
   // the same update (plain or paired schedule) on the FP64 tensor instruction (shift_dmma.cuh); nullptr
-  // where it is not built (N not a multiple of 4).  paired = 0: every system every iteration.
+  // where it is not built (N not a multiple of 4).  schedule: 0 plain, 1 alternating, 2 staggered
+  // (build_shift_items; 2 wants Q = this iteration's Q field, Qprev = the previous iteration's).
   int (*shift_update_dmma)(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                            const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
-                           int sms, int* launches, int paired);
+                           int sms, int* launches, int schedule);
   int (*max_partials)(int sms);
   // sites that must be allocated after site 0 of every field / of the links (>= V + 2): the
   // tensor-map views of the chain stencil are rectangular and reach past the end of the field
@@ -182,6 +186,12 @@ struct Ops {
   static constexpr bool DMMA_N = (N % 4 == 0);
   using SDG = ShiftDmmaGeom<DMMA_N ? N : 4, SHIFT_TS>;
   static constexpr bool DMMA_OK = DMMA_N && SDG::SMEM_BYTES <= 227 * 1024 && 2 * SDG::PAIR <= 256;
+  // experimental shapes of the same kernel (BCG_DMMA_CFG = 1: 32 sites x 3 stages, one CTA per SM;
+  // 2: 64 sites x 2 stages, eight compute warps in one CTA per SM)
+  using SDG1 = ShiftDmmaGeom<DMMA_N ? N : 4, 32, 3>;
+  using SDG2 = ShiftDmmaGeom<DMMA_N ? N : 4, 64, 2>;
+  static constexpr bool DMMA_CFG1 = DMMA_OK && N <= 12 && SDG1::SMEM_BYTES <= 227 * 1024;
+  static constexpr bool DMMA_CFG2 = DMMA_OK && N <= 12 && SDG2::SMEM_BYTES <= 227 * 1024;
   static constexpr bool APIPE = (N % 2 == 0 && N >= 4 && N <= 12);  // pipelined Q += T*M (axpy_pipe.cuh)
   static constexpr int APIPE_TS = 32;
   using APG = AxpyPipeGeom<APIPE ? N : 4, APIPE_TS>;
@@ -194,7 +204,7 @@ struct Ops {
   // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
   // outside any stream capture -- and used to size the persistent grids.
   struct Caps {
-    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0, dmma = 0;
+    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0, dmma = 0, dmma1 = 0, dmma2 = 0;
   };
   // Both the shared-memory opt-ins (cudaFuncSetAttribute) and the occupancy figures are per
   // DEVICE: one slot per device ordinal, filled under a lock the first time a context of that
@@ -223,7 +233,9 @@ struct Ops {
     c.shift = occupancy_blocks(shift_update_kernel<N, kNT>, kNT, SHIFT_SMEM, sms);
     if constexpr (PIPE_OK) c.pipe = occupancy_blocks(shift_pipe_kernel<N, SHIFT_TS>, SG::NT, SG::SMEM_BYTES, sms);
     if constexpr (PAIR_OK) c.pair = occupancy_blocks(shift_pair_kernel<N, SHIFT_TS>, SG::NT, SPG::SMEM_BYTES, sms);
-    if constexpr (DMMA_OK) c.dmma = occupancy_blocks(shift_dmma_kernel<N, SHIFT_TS>, SDG::NT, SDG::SMEM_BYTES, sms);
+    if constexpr (DMMA_OK) c.dmma = occupancy_blocks(shift_dmma_kernel<N, SHIFT_TS, 2>, SDG::NT, SDG::SMEM_BYTES, sms);
+    if constexpr (DMMA_CFG1) c.dmma1 = occupancy_blocks(shift_dmma_kernel<N, 32, 3>, SDG1::NT, SDG1::SMEM_BYTES, sms);
+    if constexpr (DMMA_CFG2) c.dmma2 = occupancy_blocks(shift_dmma_kernel<N, 64, 2>, SDG2::NT, SDG2::SMEM_BYTES, sms);
     if constexpr (APIPE) {
       cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)APG::SMEM_BYTES);
@@ -354,21 +366,25 @@ struct Ops {
   }
 
   static int axpy_gram(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
-                       const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers) {
+                       const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers, cd* Qout) {
     GramPeers pe;
     if (peers) pe = *peers; else std::memset(&pe, 0, sizeof pe);
-    if (force_v1() & 2) return axpy_gram_v1(st, Q, T, M, V, gpart, ctrl, sms, launches);
+    if constexpr (!APIPE) {
+      if (Qout != nullptr && Qout != Q) return -static_cast<int>(cudaErrorNotSupported);
+    }
+    if ((force_v1() & 2) && (Qout == nullptr || Qout == Q)) return axpy_gram_v1(st, Q, T, M, V, gpart, ctrl, sms, launches);
     if constexpr (APIPE) {
       prepare(sms);
-      alignas(64) CUtensorMap tmQ, tmT;
+      alignas(64) CUtensorMap tmQ, tmQo, tmT;
       int e = make_pair_map(&tmQ, Q, 3 * N, APG::PAIR, (V + 1) / 2, APIPE_TS / 2);
+      if (!e) e = make_pair_map(&tmQo, Qout ? Qout : Q, 3 * N, APG::PAIR, (V + 1) / 2, APIPE_TS / 2);
       if (!e) e = make_pair_map(&tmT, T, 3 * N, APG::PAIR, (V + 1) / 2, APIPE_TS / 2);
       if (e) return e;
       const int grid = clamp_grid((V + APIPE_TS - 1) / APIPE_TS, sms);
       if (gpart != nullptr)
-        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
       else
-        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmT, M, V, nullptr, ctrl, pe, axpy_reverse());
+        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, nullptr, ctrl, pe, axpy_reverse());
       if (launches) ++*launches;
       e = err();
       return e ? e : (gpart != nullptr ? 1 : 0);
@@ -470,30 +486,48 @@ struct Ops {
     return -static_cast<int>(cudaErrorNotSupported);
   }
 
+  template <int TSX, int NSTX>
+  static int launch_dmma(cudaStream_t st, int cap, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
+                         const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
+                         int* launches, int paired) {
+    using G = ShiftDmmaGeom<N, TSX, NSTX>;
+    const int grid = clamp_grid((V + TSX - 1) / TSX, cap);
+    alignas(64) ShiftPairMaps maps;
+    const long long npairs = (V + 1) / 2;
+    int e = make_pair_map(&maps.Q, Q, 3 * N, G::PAIR, npairs, TSX / 2);
+    if (!e) e = make_pair_map(&maps.Qprev, Qprev ? Qprev : Q, 3 * N, G::PAIR, npairs, TSX / 2);
+    for (int s = 0; s < kMaxShifts && !e; ++s) {
+      if (fp->P[s] == nullptr || fp->X[s] == nullptr) {
+        maps.P[s] = maps.Q;  // never used: the device loop stops at the active count
+        maps.X[s] = maps.Q;
+        continue;
+      }
+      e = make_pair_map(&maps.P[s], fp->P[s], 3 * N, G::PAIR, npairs, TSX / 2);
+      if (!e) e = make_pair_map(&maps.X[s], fp->X[s], 3 * N, G::PAIR, npairs, TSX / 2);
+    }
+    if (e) return e;
+    shift_dmma_kernel<N, TSX, NSTX><<<grid, G::NT, G::SMEM_BYTES, st>>>(maps, Rm, A_odd, B_odd, A_even, B_even, V, ctrl,
+                                                                      paired);
+    if (launches) ++*launches;
+    return err();
+  }
+  static int dmma_cfg() {
+    const char* e = std::getenv("BCG_DMMA_CFG");  // read per launch: A/B runs in one process
+    return e ? std::atoi(e) : 0;
+  }
   static int shift_update_dmma(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                                const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
                                int sms, int* launches, int paired) {
     if constexpr (DMMA_OK) {
       prepare(sms);
-      const int grid = clamp_grid((V + SHIFT_TS - 1) / SHIFT_TS, caps().dmma);
-      alignas(64) ShiftPairMaps maps;
-      const long long npairs = (V + 1) / 2;
-      int e = make_pair_map(&maps.Q, Q, 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
-      if (!e) e = make_pair_map(&maps.Qprev, Qprev ? Qprev : Q, 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
-      for (int s = 0; s < kMaxShifts && !e; ++s) {
-        if (fp->P[s] == nullptr || fp->X[s] == nullptr) {
-          maps.P[s] = maps.Q;  // never used: the device loop stops at the active count
-          maps.X[s] = maps.Q;
-          continue;
-        }
-        e = make_pair_map(&maps.P[s], fp->P[s], 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
-        if (!e) e = make_pair_map(&maps.X[s], fp->X[s], 3 * N, SDG::PAIR, npairs, SHIFT_TS / 2);
-      }
-      if (e) return e;
-      shift_dmma_kernel<N, SHIFT_TS><<<grid, SDG::NT, SDG::SMEM_BYTES, st>>>(maps, Rm, A_odd, B_odd, A_even, B_even, V,
-                                                                             ctrl, paired);
-      if (launches) ++*launches;
-      return err();
+      const int cfg = dmma_cfg();
+      if constexpr (DMMA_CFG1)
+        if (cfg == 1)
+          return launch_dmma<32, 3>(st, caps().dmma1, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired);
+      if constexpr (DMMA_CFG2)
+        if (cfg == 2)
+          return launch_dmma<64, 2>(st, caps().dmma2, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired);
+      return launch_dmma<SHIFT_TS, 2>(st, caps().dmma, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired);
     }
     return -static_cast<int>(cudaErrorNotSupported);
   }
@@ -523,6 +557,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::dirac4_sweep,
                              &Ops<N>::gram,
                              &Ops<N>::axpy_gram,
+                             Ops<N>::APIPE ? 1 : 0,
                              (Ops<N>::CHAIN && Ops<N>::APIPE) ? 1 : 0,
                              &Ops<N>::axpy_gram_v1,
                              &Ops<N>::rescale_add,

@@ -36,7 +36,7 @@
 
 namespace bcg {
 
-template <int N, int TS>
+template <int N, int TS, int NST = 2>
 struct ShiftDmmaGeom {
   static_assert(N % 4 == 0, "the real-expanded product needs 2N a multiple of 8");
   static constexpr int NSPLIT = shift_nsplit(N), JC = N / NSPLIT;  // layout of the coefficient operands (shift_mat_index)
@@ -52,7 +52,7 @@ struct ShiftDmmaGeom {
   static constexpr int PAIR = 2 * SITE + ((2 - (2 * SITE) % 8 + 8) % 8);
   static constexpr int TILE = (TS / 2) * PAIR;
   static constexpr int KS = N / 2, NTL = N / 4;  // k-steps, n-tiles of one product
-  static constexpr int NSTAGE = 2;
+  static constexpr int NSTAGE = NST;
   static constexpr int STAGE_ELEMS = (2 * TILE + 4 * N * N + 7) / 8 * 8;  // P, X tiles + (A', B', A, B)
   static constexpr int SCRATCH = 3 * NTL * NCT;                           // Qprev words, [word][thread]
   static constexpr size_t SMEM_BYTES = sizeof(cd) * (NSTAGE * STAGE_ELEMS + SCRATCH) + 64;
@@ -94,30 +94,29 @@ __device__ __forceinline__ void load_coef_frags(const cd* __restrict__ sM, int l
   }
 }
 
-template <int N, int TS>
-__global__ void __maxnreg__((ShiftDmmaGeom<N, TS>::MAXREG))
+template <int N, int TS, int NST>
+__global__ void __maxnreg__((ShiftDmmaGeom<N, TS, NST>::MAXREG))
 shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restrict__ Rrecip,
                   const cd* __restrict__ Aodd, const cd* __restrict__ Bodd, const cd* __restrict__ Aeven,
-                  const cd* __restrict__ Beven, long long V, const Ctrl* __restrict__ ctrl, int paired) {
+                  const cd* __restrict__ Beven, long long V, const Ctrl* __restrict__ ctrl, int schedule) {
   // Aodd/Bodd: operand slots written in odd iterations, Aeven/Beven: in even ones ([shift][N*N] each;
   // the same slots when the schedule is not paired)
-  using Geo = ShiftDmmaGeom<N, TS>;
+  using Geo = ShiftDmmaGeom<N, TS, NST>;
+  constexpr int NS = Geo::NSTAGE;
   constexpr int NCW = Geo::NCW, SITE = Geo::SITE, PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE_ELEMS;
   constexpr int NN = N * N, KS = Geo::KS, NTL = Geo::NTL;
   if (ctrl->done) return;
   const int iter = ctrl->iter;
   const bool odd = (iter & 1) != 0;
-  PairPlan plan;
-  {
-    const ShiftLaunchPlan lp = shift_launch_plan(paired != 0, iter, ctrl->stop, ctrl->n_unconv, ctrl->n_act[1]);
-    plan.mode = lp.mode;
-    plan.n2 = lp.n2;
-    plan.n_items = (lp.mode == 1) ? 2 : (lp.mode == 2) ? 2 + lp.n1 : 1 + lp.n2;
-  }
   const cd* Acur = odd ? Aodd : Aeven;
   const cd* Bcur = odd ? Bodd : Beven;
-  const cd* Aprev = Aodd;  // only used in even iterations of the paired schedule
-  const cd* Bprev = Bodd;
+  const cd* Aprev = odd ? Aeven : Aodd;  // operands the previous iteration left in the other parity's slots
+  const cd* Bprev = odd ? Beven : Bodd;
+  // the items of a tile (same list in every thread: built once, read from shared memory)
+  __shared__ ShiftItem s_items[kMaxShiftItems];
+  __shared__ int s_n_items;
+  if (threadIdx.x == 0)
+    s_n_items = build_shift_items(schedule, iter, ctrl->stop, ctrl->n_unconv, ctrl->n_act[(iter - 1) & 1], s_items, nullptr);
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* sbuf = reinterpret_cast<cd*>(smem_raw);
@@ -138,12 +137,18 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
   const long long ntiles = (V + TS - 1) / TS;
   constexpr uint32_t MAT_BYTES = NN * sizeof(cd);
   constexpr uint32_t TILE_BYTES = TILE * sizeof(cd);
+  const int n_items = s_n_items;
 
   if (warp == NCW) {
     // ===================== producer (as shift_pair_kernel) =====================
     if (lane != 0) return;
     long long it = 0;
-    int d_pair[2] = {0, 0}, d_kind[2] = {KQPREV, KQPREV}, d_s[2] = {-1, -1};  // items in flight
+    int d_pair[NS], d_kind[NS], d_s[NS];  // items in flight
+    for (int i = 0; i < NS; ++i) {
+      d_pair[i] = 0;
+      d_kind[i] = KQPREV;
+      d_s[i] = -1;
+    }
     auto store_item = [&](int st) {
       const cd* buf = sbuf + st * STAGE;
       const int kind = d_kind[st], s = d_s[st], pr = d_pair[st];
@@ -158,16 +163,15 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
     };
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int pair0 = static_cast<int>(tile * (TS / 2));
-      for (int k = 0; k < plan.n_items; ++k, ++it) {
-        const int st = static_cast<int>(it & 1);
-        const uint32_t use = static_cast<uint32_t>(it >> 1);
-        if (it >= 2) {
-          mbar_wait(computed + st, (use - 1) & 1u);  // item it-2 has been computed in place
+      for (int k = 0; k < n_items; ++k, ++it) {
+        const int st = static_cast<int>(it % NS);
+        const uint32_t use = static_cast<uint32_t>(it / NS);
+        if (it >= NS) {
+          mbar_wait(computed + st, (use - 1) & 1u);  // item it-NS has been computed in place
           store_item(st);
           bulk_wait_read0();
         }
-        int kind, s;
-        plan.item(k, kind, s);
+        const int kind = s_items[k].kind, s = s_items[k].s;
         d_pair[st] = pair0;
         d_kind[st] = kind;
         d_s[st] = s;
@@ -196,9 +200,9 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
         }
       }
     }
-    for (long long k = (it >= 2 ? it - 2 : 0); k < it; ++k) {  // drain the last (up to two) items
-      const int st = static_cast<int>(k & 1);
-      mbar_wait(computed + st, static_cast<uint32_t>(k >> 1) & 1u);
+    for (long long k = (it >= NS ? it - NS : 0); k < it; ++k) {  // drain the last (up to NS) items
+      const int st = static_cast<int>(k % NS);
+      mbar_wait(computed + st, static_cast<uint32_t>(k / NS) & 1u);
       store_item(st);
     }
     bulk_wait0();
@@ -217,11 +221,10 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
     const int ns = static_cast<int>(min(static_cast<long long>(TS), V - x0));
     const bool live = lsite < ns;
     cd qf[3][NTL];  // this lane's C-fragment positions of the new Q: (colour c, column 4 jt + q)
-    for (int k = 0; k < plan.n_items; ++k, ++it) {
-      int kind, s;
-      plan.item(k, kind, s);
-      const int st = static_cast<int>(it & 1);
-      mbar_wait(full + st, static_cast<uint32_t>(it >> 1) & 1u);
+    for (int k = 0; k < n_items; ++k, ++it) {
+      const int kind = s_items[k].kind;
+      const int st = static_cast<int>(it % NS);
+      mbar_wait(full + st, static_cast<uint32_t>(it / NS) & 1u);
       cd* buf = sbuf + st * STAGE;
       if (kind == KQ || kind == KQ_KEEP) {
         if (q < 3 && live) {

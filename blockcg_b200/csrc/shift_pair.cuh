@@ -45,8 +45,6 @@ struct ShiftPairMaps {
   CUtensorMap X[kMaxShifts];
 };
 
-enum : int { KQ = 0, KQ_KEEP = 1, KQPREV = 2, KCUR = 3, KPREV = 4, KBOTH = 5 };
-
 // What the k-th item of a tile is.  mode 0: plain (Q, then every active shift); 1: first of a
 // pair (Q kept, shift 0); 2: second of a pair (Q, Qprev, shift 0, shifted systems).
 struct PairPlan {
@@ -83,10 +81,19 @@ shift_pair_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
   const bool odd = (iter & 1) != 0;
   PairPlan plan;
   {
-    const ShiftLaunchPlan lp = shift_launch_plan(true, iter, ctrl->stop, ctrl->n_unconv, ctrl->n_act[1]);
-    plan.mode = lp.mode;
-    plan.n2 = lp.n2;
-    plan.n_items = (lp.mode == 1) ? 2 : (lp.mode == 2) ? 2 + lp.n1 : 1 + lp.n2;
+    // the alternating schedule of build_shift_items(), in closed form
+    const int n2 = ctrl->n_unconv, n1 = odd ? n2 : ctrl->n_act[1];
+    plan.n2 = n2;
+    if (odd && !ctrl->stop && n1 > 1) {
+      plan.mode = 1;
+      plan.n_items = 2;
+    } else if (!odd && n1 > 1) {
+      plan.mode = 2;
+      plan.n_items = 2 + n1;
+    } else {
+      plan.mode = 0;
+      plan.n_items = 1 + n2;
+    }
   }
   const cd* Acur = odd ? Aodd : Aeven;
   const cd* Bcur = odd ? Bodd : Beven;

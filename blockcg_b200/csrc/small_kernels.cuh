@@ -39,7 +39,7 @@ struct MatLayout {
   __host__ __device__ size_t beta_s(int s) const { return (M_FIXED_COUNT + 3 * S + s) * nn(); }
   // paired multishift update (shift_pair.cuh): the operands of odd iterations live in a second set of
   // slots, so that the even iteration's launch still finds them
-  int pair = 0;
+  int pair = 0;  // schedule of the multishift update: 0 plain, 1 alternating, 2 staggered (build_shift_items)
   __host__ __device__ size_t A(int s, int iter) const { return ((pair && (iter & 1)) ? M_FIXED_COUNT + 4 * S + s : M_FIXED_COUNT + s) * nn(); }
   __host__ __device__ size_t B(int s, int iter) const { return ((pair && (iter & 1)) ? M_FIXED_COUNT + 5 * S + s : M_FIXED_COUNT + S + s) * nn(); }
   __host__ __device__ size_t total() const { return (M_FIXED_COUNT + 6 * S) * nn(); }
@@ -747,8 +747,9 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
       // statistics: systems updated in this iteration, bytes the multishift launch that follows will move
       const int na = ctrl->n_unconv;
       ctrl->hist[na < 0 ? 0 : (na > kMaxShifts ? kMaxShifts : na)] += 1u;
-      ctrl->shift_passes += static_cast<unsigned long long>(
-          shift_launch_plan(L.pair != 0, iter, stop, na, ctrl->n_act[1]).passes());
+      int passes = 0;
+      build_shift_items(L.pair, iter, stop, na, ctrl->n_act[(iter - 1) & 1], nullptr, &passes);
+      ctrl->shift_passes += static_cast<unsigned long long>(passes);
     }
     return;
   }

@@ -189,6 +189,17 @@ typedef struct {
 } bcg_solve_stats;
 int bcg_last_solve_stats(bcg_ctx* ctx, bcg_solve_stats* out);
 
+/* The schedule of the multishift update, as the kernels evaluate it on the device from the loop's control
+ * block (host-side copy of the same function; needs no device): schedule 0 = every active system in every
+ * iteration (the reference's order, block_solvers.hpp:161-182), 1 = shifted systems served every second
+ * iteration with both pending updates, 2 = the same, odd-numbered systems in odd and even-numbered systems in
+ * even iterations.  A system's updates are always applied in iteration order with the coefficients and the Q
+ * of their own iteration, so all three produce identical bits.  kinds[i]: 0 Q <- Q rho^-1, 1 the same and kept
+ * as the previous Q, 2 previous Q read, 3 / 4 / 5: system systems[i] gets this / the previous / both
+ * iterations' updates.  Returns the number of items (<= BCG_MAX_SHIFTS + 2). */
+int bcg_shift_schedule(int schedule, int iteration, int stop, int n_active, int n_active_prev, int* kinds, int* systems,
+                       int* field_passes);
+
 /* In-loop profile: n_iterations (<= 4096) of the NEXT solve on this context, starting once at least
  * after_iterations have run (so the GPU is at its sustained clocks), are submitted kernel by kernel with a
  * CUDA event after each stage instead of as graph batches; the solve is otherwise unchanged.  ms[] = mean

@@ -95,3 +95,53 @@ def test_makefile_tracks_every_header():
     want = {os.path.basename(f) for f in glob.glob(os.path.join(csrc, "*.cuh")) + glob.glob(os.path.join(csrc, "*.h"))}
     assert want <= have, sorted(want - have)
 
+
+
+def test_update_schedules_apply_every_update_once_and_in_order():
+    """The three schedules of the multishift update (bcg_shift_schedule = the function the kernels evaluate on
+    the device): simulate whole solves with random retirements (highest system first, as
+    block_solvers.hpp:161,179-181) and random stopping points, and check that every system receives the update
+    of every iteration in which it was active exactly once, in iteration order, and that a deferred update is
+    only ever applied together with the Q of its own iteration (kept as "previous Q")."""
+    import random
+
+    from blockcg_b200.capi import shift_schedule
+    KQ, KQ_KEEP, KQPREV, KCUR, KPREV, KBOTH = range(6)
+    rng = random.Random(7)
+    for trial in range(300):
+        S = rng.randint(1, 9)
+        n_it = rng.randint(1, 40)
+        # active counts per iteration: non-increasing, >= 1
+        act, a = [], S
+        for i in range(n_it):
+            act.append(a)
+            if a > 1 and rng.random() < 0.15:
+                a -= rng.randint(1, min(2, a - 1))
+        want = {s: [i + 1 for i in range(n_it) if s < act[i]] for s in range(S)}
+        for sched in (0, 1, 2):
+            got = {s: [] for s in range(S)}
+            kept = None   # iteration whose Q is available as "previous Q"
+            total = 0
+            for i in range(1, n_it + 1):
+                items, passes = shift_schedule(sched, i, i == n_it, act[i - 1], act[i - 2] if i >= 2 else 0)
+                total += passes
+                kinds = [k for k, _ in items]
+                assert kinds[0] in (KQ, KQ_KEEP) and kinds.count(KQ) + kinds.count(KQ_KEEP) == 1
+                have_prev = KQPREV in kinds
+                nsys = 0
+                for k, s in items:
+                    if k in (KPREV, KBOTH):
+                        assert have_prev and i >= 2
+                        assert kept == i - 1 or sched == 2   # alternating: the odd iteration's Q was kept
+                        got[s].append(i - 1)
+                    if k in (KCUR, KBOTH):
+                        got[s].append(i)
+                    nsys += k in (KCUR, KPREV, KBOTH)
+                if kinds[0] == KQ_KEEP:
+                    kept = i
+                assert passes == (3 if (have_prev or kinds[0] == KQ_KEEP) else 2) + 4 * nsys
+            assert got == want, (sched, S, act, got, want)
+            if sched == 0:
+                plain = total
+            else:
+                assert total <= plain + 2 * n_it   # deferring never moves more than the plain loop (+ the kept Q)

@@ -290,7 +290,7 @@ def test_paired_multishift_update_is_bit_identical(bcg, oracle, V, N, max_it, ep
     shifts = [0.0, 1e-4, 1e-2, 0.1, 0.5, 0.9]
     U, B = oracle.make_inputs(V, N, 5)
     out = {}
-    for mode in ("0", "1"):
+    for mode in ("0", "1", "2"):   # plain, alternating, staggered schedule (build_shift_items)
         monkeypatch.setenv("BCG_PAIR", mode)
         with bcg.Context(V, N, max_shifts=len(shifts)) as ctx:
             ctx.set_links(U, mass)
@@ -298,13 +298,14 @@ def test_paired_multishift_update_is_bit_identical(bcg, oracle, V, N, max_it, ep
             xs = [ctx.field() for _ in shifts]
             info = ctx.solve_sbcgrq_dev(xs, hb, shifts, eps, eps_shifts, max_it)
             out[mode] = (info.iterations, info.n_unconverged, [ctx.download(h) for h in xs])
-    assert out["0"][0] == out["1"][0] and out["0"][1] == out["1"][1]
+    for mode in ("1", "2"):
+        assert out["0"][0] == out[mode][0] and out["0"][1] == out[mode][1]
+        for a, b in zip(out["0"][2], out[mode][2]):
+            assert np.array_equal(a, b), mode
     if max_it > 1000:
         assert out["0"][1] < len(shifts)  # some shifted systems did retire before the end
     if eps_shifts > 1e-6:
         assert out["0"][1] == 1
-    for a, b in zip(out["0"][2], out["1"][2]):
-        assert np.array_equal(a, b)
 
 
 def test_inputs_generated_on_device(bcg, oracle):
@@ -495,7 +496,7 @@ def test_solve_statistics(bcg, oracle):
     V, N, mass, eps = 1000, 12, 0.02, 1e-10
     shifts = [0.0, 1e-4, 1e-2, 0.1, 0.5, 0.9]
     U, B = oracle.make_inputs(V, N, 5)
-    for pair in ("0", "1"):
+    for pair in ("0", "1", "2"):
         os.environ["BCG_PAIR"] = pair
         try:
             with bcg.Context(V, N, max_shifts=len(shifts)) as ctx:
@@ -509,7 +510,7 @@ def test_solve_statistics(bcg, oracle):
         h = st["active_hist"]
         assert sum(h) == info.iterations == st["iterations"]
         assert h[len(shifts)] > 0 and sum(h[len(shifts) + 1:]) == 0 and h[0] == 0
-        assert st["paired"] == (pair == "1")
+        assert st["paired"] == (pair != "0")
         plain = sum((2 + 4 * a) * n for a, n in enumerate(h))
         if pair == "0":
             assert st["shift_update_field_passes"] == plain
