@@ -41,7 +41,8 @@ struct AxpyPipeGeom {
   static constexpr int ROWS = 3 * TS;
 };
 
-template <int N, int TS, bool GRAM>
+// GRAM: 0 none, 1 four Gram warps with DFMA (GramPart), 2 the same warps on the FP64 tensor instruction (GramDmma)
+template <int N, int TS, int GRAM>
 __global__ void __launch_bounds__(AxpyPipeGeom<N, TS>::NT, 1)
 axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQout,
                  const __grid_constant__ CUtensorMap tmT,
@@ -121,6 +122,31 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp >= NCW) {
     // ===================== Gram warps =====================
     if (!GRAM) return;
+    if constexpr (GRAM == 2 && N % 4 == 0) {
+      // row quad = site pairs 4 gw .. 4 gw + 3 of the tile at one (site-in-pair sp, colour c); the four Gram
+      // warps split the TS / 2 = 16 pairs, each takes all six (sp, c)
+      static_assert(TS == 32, "the tensor-instruction Gram splits 16 site pairs over four warps");
+      const int gw = warp - NCW, q = lane & 3, mm = lane >> 2;
+      const int off = 2 * ((4 * gw + q) * PAIR) + 6 * (mm >> 1) + (mm & 1);
+      GramDmma<N> gd;
+      gd.init();
+      for (int i = 0; i < nmine; ++i) {
+        const int st = i % NS;
+        mbar_wait(cdone + st, static_cast<uint32_t>((i / NS) & 1));
+        const double* dQ = reinterpret_cast<const double*>(sbuf + st * STAGE + TILE) + off;
+        const long long site = 2LL * tile_pair0(i) + 2 * (4 * gw + q);  // first site of this lane's pair
+#pragma unroll
+        for (int sc = 0; sc < 6; ++sc) {
+          const int sp = sc / 3, c = sc - 3 * sp;
+          gd.quad(dQ + 2 * (sp * SITE + c), dQ + 2 * (sp * SITE + c), site + sp < V);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gdone + st);
+      }
+      gd.store(gpart + (static_cast<size_t>(kGramRawOff) + blockIdx.x) * N * N, sbuf, gw);
+      gram_group_reduce<N>(gpart, gw, peers, ctrl, 1);
+      return;
+    }
     // row = (colour c, site-in-pair sp, pair m), m fastest across lanes: 8 consecutive pairs start
     // on 8 different 16-byte bank groups
     auto gram_loop = [&](auto& part) {

@@ -112,6 +112,79 @@ struct GramPart {
   }
 };
 
+// ---- the same lower triangle on the FP64 tensor instruction (mma.sync.m8n8k4.f64, SASS DMMA) -------
+// G = A^dag B as a real product over rows:  S[(i,pi)][(j,pj)] = sum_rows A[row][i].pi * B[row][j].pj
+// (2N x 2N real, parts interleaved: real index 2 i + part), then  Re G_ij = S(i0,j0) + S(i1,j1),
+// Im G_ij = S(i0,j1) - S(i1,j0).  One instruction takes K = 4 rows and an 8 x 8 tile of S (4 x 4 complex
+// entries); only tiles on or below the diagonal are computed (N/4 (N/4 + 1) / 2 of them: 6 at N = 12, i.e.
+// 384 multiply-adds per row against 312 for the exact triangle) -- a few more flops on the same FP64 pipe,
+// but 1.5 DMMA + 1.5 LDS.64 per row instead of ~10 DFMA + 0.4 LDS.128 per row and lane: the Gram warps stop
+// competing with the stencil warps for issue slots, and their six accumulation chains are independent.
+// Lane (q = lane % 4, mm = lane / 4): A fragment = A[row q][real column 8 mt + mm], B fragment likewise.
+template <int N>
+struct GramDmma {
+  static_assert(N % 4 == 0, "GramDmma needs N a multiple of 4");
+  static constexpr int NB = N / 4;
+  static constexpr int NTILE = NB * (NB + 1) / 2;
+  double acc[NTILE][2];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) acc[t][0] = acc[t][1] = 0.0;
+  }
+  // pa / pb: this lane's double of tile 0 in row q of the quad (column block t is 24 doubles = 4 complex
+  // columns x 3 colours further on); rows outside the field contribute zero
+  __device__ __forceinline__ void quad(const double* __restrict__ pa, const double* __restrict__ pb, bool valid) {
+    double a[NB], b[NB];
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      double va, vb;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(va) : "r"(smem_u32(pa + 24 * t)));
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vb) : "r"(smem_u32(pb + 24 * t)));
+      a[t] = valid ? va : 0.0;
+      b[t] = valid ? vb : 0.0;
+    }
+    int idx = 0;
+#pragma unroll
+    for (int mt = 0; mt < NB; ++mt)
+#pragma unroll
+      for (int nt = 0; nt <= mt; ++nt) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(acc[idx][0]), "+d"(acc[idx][1])
+                     : "d"(a[mt]), "d"(b[nt]));
+        ++idx;
+      }
+  }
+  // Combine the (re, im) parts across lane pairs, park this warp's tiles in `scratch` ([4 warps][N*N] complex,
+  // shared by the four Gram warps), then the 128 threads add the four blocks in warp order (fixed =>
+  // deterministic) and write the lower block triangle of the N x N column-major block.
+  __device__ __forceinline__ void store(cd* __restrict__ dstNN, cd* __restrict__ scratch, int gw) {
+    const int lane = threadIdx.x & 31;
+    int idx = 0;
+#pragma unroll
+    for (int mt = 0; mt < NB; ++mt)
+#pragma unroll
+      for (int nt = 0; nt <= mt; ++nt) {
+        const double o0 = __shfl_xor_sync(0xffffffffu, acc[idx][0], 4);
+        const double o1 = __shfl_xor_sync(0xffffffffu, acc[idx][1], 4);
+        if (((lane >> 2) & 1) == 0) {
+          const int i = 4 * mt + (lane >> 3), j = 4 * nt + (lane & 3);
+          scratch[gw * N * N + i + N * j] = cmake(acc[idx][0] + o1, acc[idx][1] - o0);
+        }
+        ++idx;
+      }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+    for (int e = gw * 32 + lane; e < N * N; e += 128) {
+      const int i = e % N, j = e / N;
+      if (i / 4 < j / 4) continue;  // block above the diagonal: never produced, never consumed
+      cd sum = scratch[e];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) sum = cadd(sum, scratch[w * N * N + e]);
+      dstNN[e] = sum;
+    }
+  }
+};
+
 // ---- second level of the Gram reduction, inside the producing kernel ---------------------------
 // The per-CTA partial blocks are not handed to the coefficient kernel one by one (a single CTA
 // pulling ~150 blocks out of L2 is a 5-10 us latency chain in every iteration): CTAs form groups
@@ -242,7 +315,8 @@ struct ChainGeom {
   static constexpr bool PARITY_INNER = (G != 4) || (SITE % 8 == 4);
 };
 
-// GMODE 0: no Gram.  1: four dedicated Gram warps working one tile behind the stencil warps.
+// GMODE 0: no Gram.  1: four dedicated Gram warps working one tile behind the stencil warps (DFMA, GramPart).
+// 3: the same four warps on the FP64 tensor instruction (GramDmma).
 // 2 (experiment, not built by default): no dedicated warps -- after each tile the four stencil
 // warps wait for one another and compute one GramPart each over the tile they have just
 // finished, accumulators in their own registers (255 per thread with 6 warps per CTA).  Measured
@@ -275,7 +349,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (tid == 0) {
     for (int i = 0; i < Geo::NBAR_IN; ++i) mbar_init(inb + i, 1);
     for (int i = 0; i < SO; ++i) mbar_init(ofull + i, Geo::NSW);
-    for (int i = 0; i < Geo::NBAR_G; ++i) mbar_init(gdone + i, GMODE == 1 ? Geo::NGW : Geo::NSW);
+    for (int i = 0; i < Geo::NBAR_G; ++i) mbar_init(gdone + i, (GMODE == 1 || GMODE == 3) ? Geo::NGW : Geo::NSW);
     for (int i = 0; i < SO; ++i) mbar_init(sdone + i, 1);
     mbar_fence_init();
   }
@@ -329,6 +403,32 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
   if (warp >= Geo::NSW) {
     // ===================== Gram warps: block (ti,tj) of P^dag T =====================
+    if constexpr (GMODE == 3) {
+      // row quad = sub-chains 4 gw .. 4 gw + 3 at one (site s of the window, colour c): lane q = lane % 4 reads
+      // sub-chain 4 gw + q; the four Gram warps split the K = 16 sub-chains, each takes all W * 3 (s, c)
+      static_assert(K == 16, "the tensor-instruction Gram splits 16 sub-chains over four warps");
+      const int gw = warp - Geo::NSW, q = lane & 3, mm = lane >> 2;
+      const int kch = 4 * gw + q;
+      const long long rem = chain_end(kch) - chain_start(kch);  // sites of this lane's sub-chain (<= 0: empty)
+      const int off = 2 * (kch * PP) + 6 * (mm >> 1) + (mm & 1);
+      GramDmma<N> gd;
+      gd.init();
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(ofull + (t % SO), static_cast<uint32_t>((t / SO) & 1));
+        const double* dP = reinterpret_cast<const double*>(sP + (t % SP) * (K * PP)) + off;
+        const double* dO = reinterpret_cast<const double*>(sO + (t % SO) * (K * PP)) + off;
+#pragma unroll
+        for (int sc = 0; sc < 3 * W; ++sc) {
+          const int s = sc / 3, c = sc - 3 * s;
+          gd.quad(dP + 2 * (s * SITE + c), dO + 2 * (s * SITE + c), t * W + s < rem);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gdone + (t & 3));
+      }
+      gd.store(gpart + (static_cast<size_t>(kGramRawOff) + blockIdx.x) * N * N, sP + ((T + 1) % SP) * (K * PP), gw);
+      gram_group_reduce<N>(gpart, gw, peers, ctrl, 0);
+      return;
+    }
     if (GMODE != 1) return;
     // row = (colour c, site s of the window, sub-chain k), k fastest across lanes: the 8 lanes of a
     // quarter warp read 8 consecutive windows, which start on 8 different 16-byte bank groups
@@ -426,7 +526,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     for (int t = 0; t < T; ++t) {
       mbar_wait(inb + (t & 3), static_cast<uint32_t>((t >> 2) & 1));
       if (t >= SO) {  // T window slot free again: Gram and store of tile t-SO are through with it
-        if (GMODE == 1) mbar_wait(gdone + ((t - SO) & 3), static_cast<uint32_t>(((t - SO) >> 2) & 1));
+        if (GMODE == 1 || GMODE == 3) mbar_wait(gdone + ((t - SO) & 3), static_cast<uint32_t>(((t - SO) >> 2) & 1));
         mbar_wait(sdone + (t % SO), static_cast<uint32_t>(((t - SO) / SO) & 1));
       }
       const cd* tP0 = sP + (t % SP) * (K * PP) + k * PP;         // P at out sites o0 .. o0+W

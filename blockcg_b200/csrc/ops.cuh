@@ -144,6 +144,13 @@ inline int force_v1() {
 #define BCG_CHAIN_GMODE 1
 #endif
 
+// fused Gram epilogues of the stencil and of Q += T*M on the FP64 tensor instruction (GramDmma, dirac_chain.cuh);
+// BCG_GRAM_DMMA=0 selects the DFMA form (GramPart).  Read per launch: A/B runs in one process.
+inline int gram_dmma() {
+  const char* e = std::getenv("BCG_GRAM_DMMA");
+  return e ? std::atoi(e) : 1;
+}
+
 #ifdef BCG_N  // ---- per-N implementation, included only by inst.cu ----------------------------
 
 constexpr int kNT = 192;  // 6 warps: one 4x4 Gram block per warp at N = 12, whole sites per CTA
@@ -237,16 +244,22 @@ struct Ops {
     if constexpr (DMMA_CFG1) c.dmma1 = occupancy_blocks(shift_dmma_kernel<N, 32, 3>, SDG1::NT, SDG1::SMEM_BYTES, sms);
     if constexpr (DMMA_CFG2) c.dmma2 = occupancy_blocks(shift_dmma_kernel<N, 64, 2>, SDG2::NT, SDG2::SMEM_BYTES, sms);
     if constexpr (APIPE) {
-      cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)APG::SMEM_BYTES);
-      cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)APG::SMEM_BYTES);
+      if constexpr (N % 4 == 0)
+        cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)APG::SMEM_BYTES);
     }
     if constexpr (CHAIN) {
       cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, CGMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)CGm::SMEM_BYTES);
       cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)CGm::SMEM_BYTES);
+      if constexpr (N % 4 == 0 && CK == 16)
+        cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)CGm::SMEM_BYTES);
     }
   }
 
@@ -330,10 +343,19 @@ struct Ops {
       if (!e) e = make_chain_map(&tmO, out, CW * 3 * N, CW * 3 * N, CGm::PP, pl.T, pl.nchains + 1, CK);
       if (!e) e = make_chain_map(&tmU, U - 9, (CW + 2) * 9, CW * 9, CGm::PU, pl.T, pl.nchains + 1, CK);
       if (e) return e;
-      if (gpart != nullptr)
-        dirac_chain_kernel<N, CG_, CK, CW, CGMODE><<<pl.grid, CNT_G, CGm::SMEM_BYTES, st>>>(
-            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
-      else
+      if (gpart != nullptr) {
+        bool done = false;
+        if constexpr (N % 4 == 0 && CK == 16) {
+          if (gram_dmma()) {
+            dirac_chain_kernel<N, CG_, CK, CW, 3><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
+                tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
+            done = true;
+          }
+        }
+        if (!done)
+          dirac_chain_kernel<N, CG_, CK, CW, CGMODE><<<pl.grid, CNT_G, CGm::SMEM_BYTES, st>>>(
+              tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
+      } else
         dirac_chain_kernel<N, CG_, CK, CW, 0><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
             tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl, pe);
       if (launches) ++*launches;
@@ -381,10 +403,19 @@ struct Ops {
       if (!e) e = make_pair_map(&tmT, T, 3 * N, APG::PAIR, (V + 1) / 2, APIPE_TS / 2);
       if (e) return e;
       const int grid = clamp_grid((V + APIPE_TS - 1) / APIPE_TS, sms);
-      if (gpart != nullptr)
-        axpy_pipe_kernel<N, APIPE_TS, true><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
-      else
-        axpy_pipe_kernel<N, APIPE_TS, false><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, nullptr, ctrl, pe, axpy_reverse());
+      if (gpart != nullptr) {
+        bool done = false;
+        if constexpr (N % 4 == 0) {
+          if (gram_dmma()) {
+            axpy_pipe_kernel<N, APIPE_TS, 2><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+            done = true;
+          }
+        }
+        if (!done)
+          axpy_pipe_kernel<N, APIPE_TS, 1><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+      } else {
+        axpy_pipe_kernel<N, APIPE_TS, 0><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, nullptr, ctrl, pe, axpy_reverse());
+      }
       if (launches) ++*launches;
       e = err();
       return e ? e : (gpart != nullptr ? 1 : 0);

@@ -33,6 +33,9 @@ for var in variants:
         hs = [hb] + [ctx.field() for _ in range(2 * S)]
         for h in hs[1:]:
             ctx.copy(h, hb)
+        for nm, which in (("dirac_gram", 0), ("dirac", 1), ("axpy_gram", 3), ("axpy", 5)):
+            ms, _ = ctx.bench_kernel(which, 20, hs[:2], 1)
+            out[nm + "_ms"] = ms
         for a in (1, 5, 9):
             ms, _ = ctx.bench_kernel(13, 8, hs[:1 + 2 * a], a)
             out["pair_ms_per_launch[%d]" % a] = ms / 2
