@@ -147,6 +147,7 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       gram_group_reduce<N>(gpart, gw, peers, ctrl, 1);
       return;
     }
+    if constexpr (GRAM == 1) {
     // row = (colour c, site-in-pair sp, pair m), m fastest across lanes: 8 consecutive pairs start
     // on 8 different 16-byte bank groups
     auto gram_loop = [&](auto& part) {
@@ -179,6 +180,7 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       case 1: { GramPart<N, 1> part; gram_loop(part); break; }
       case 2: { GramPart<N, 2> part; gram_loop(part); break; }
       default: { GramPart<N, 3> part; gram_loop(part); break; }
+    }
     }
     return;
   }

@@ -506,6 +506,9 @@ static int ctx_create(bcg_ctx** out, int64_t v_local, const int64_t* dims, int n
   CU(cudaMemset(c->U_alloc, 0, static_cast<size_t>(c->cap + c->halo) * c->links_site * sizeof(cd)));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   for (auto& e : c->ev_batch) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if ((1 + kRedSlices) * c->L.nn() * sizeof(cd) > 48 * 1024)  // N = 32: the stand-alone Gram reduction needs the opt-in too
+    CU(cudaFuncSetAttribute(gram_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            static_cast<int>((1 + kRedSlices) * c->L.nn() * sizeof(cd))));
   c->small_smem = SmallSmem::bytes(n_rhs);
   if (c->small_smem > 48 * 1024) {
     const int b = static_cast<int>(c->small_smem);

@@ -430,6 +430,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       return;
     }
     if (GMODE != 1) return;
+    if constexpr (GMODE == 1) {
     // row = (colour c, site s of the window, sub-chain k), k fastest across lanes: the 8 lanes of a
     // quarter warp read 8 consecutive windows, which start on 8 different 16-byte bank groups
     auto gram_loop = [&](auto& part) {
@@ -463,6 +464,7 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       case 1: { GramPart<N, 1> part; gram_loop(part); break; }
       case 2: { GramPart<N, 2> part; gram_loop(part); break; }
       default: { GramPart<N, 3> part; gram_loop(part); break; }
+    }
     }
     return;
   }

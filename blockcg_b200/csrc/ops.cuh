@@ -161,7 +161,9 @@ struct Tune {
   static constexpr int R = (N % 3 == 0) ? 3 : (N % 2 == 0) ? 2 : 1;
   // parity-chain stencil (dirac_chain.cuh): column groups per site, 0 = not used at this N
   // (N = 16 would need a finer split of the Gram: 36 accumulators per warp do not fit in registers)
-  static constexpr int CHAIN_G = (N % 4 == 0 && N <= 12) ? 4 : 0;
+  // N = 16: eight column groups of two (the Gram runs on the tensor instruction there: GramDmma needs no
+  // per-entry accumulators, which is what kept the DFMA form from fitting in registers)
+  static constexpr int CHAIN_G = (N % 4 == 0 && N <= 12) ? 4 : (N == 16 ? 8 : 0);
   static constexpr int CHAIN_K = 16;  // sub-chains per CTA
   static constexpr int CHAIN_W = 2;   // sites per sub-chain and tile
 };
@@ -199,7 +201,8 @@ struct Ops {
   using SDG2 = ShiftDmmaGeom<DMMA_N ? N : 4, 64, 2>;
   static constexpr bool DMMA_CFG1 = DMMA_OK && N <= 12 && SDG1::SMEM_BYTES <= 227 * 1024;
   static constexpr bool DMMA_CFG2 = DMMA_OK && N <= 12 && SDG2::SMEM_BYTES <= 227 * 1024;
-  static constexpr bool APIPE = (N % 2 == 0 && N >= 4 && N <= 12);  // pipelined Q += T*M (axpy_pipe.cuh)
+  static constexpr bool APIPE = (N % 2 == 0 && N >= 4 && N <= 12) || N == 16;  // pipelined Q += T*M (axpy_pipe.cuh)
+  static constexpr bool DFMA_GRAM = N <= 12;  // GramPart (DFMA accumulators per entry) fits in registers
   static constexpr int APIPE_TS = 32;
   using APG = AxpyPipeGeom<APIPE ? N : 4, APIPE_TS>;
   static constexpr bool CHAIN = Tune<N>::CHAIN_G > 0;
@@ -244,8 +247,9 @@ struct Ops {
     if constexpr (DMMA_CFG1) c.dmma1 = occupancy_blocks(shift_dmma_kernel<N, 32, 3>, SDG1::NT, SDG1::SMEM_BYTES, sms);
     if constexpr (DMMA_CFG2) c.dmma2 = occupancy_blocks(shift_dmma_kernel<N, 64, 2>, SDG2::NT, SDG2::SMEM_BYTES, sms);
     if constexpr (APIPE) {
-      cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)APG::SMEM_BYTES);
+      if constexpr (DFMA_GRAM)
+        cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)APG::SMEM_BYTES);
       cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)APG::SMEM_BYTES);
       if constexpr (N % 4 == 0)
@@ -253,8 +257,9 @@ struct Ops {
                              (int)APG::SMEM_BYTES);
     }
     if constexpr (CHAIN) {
-      cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, CGMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)CGm::SMEM_BYTES);
+      if constexpr (DFMA_GRAM)
+        cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, CGMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)CGm::SMEM_BYTES);
       cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)CGm::SMEM_BYTES);
       if constexpr (N % 4 == 0 && CK == 16)
@@ -346,15 +351,17 @@ struct Ops {
       if (gpart != nullptr) {
         bool done = false;
         if constexpr (N % 4 == 0 && CK == 16) {
-          if (gram_dmma()) {
+          if (gram_dmma() || !DFMA_GRAM) {
             dirac_chain_kernel<N, CG_, CK, CW, 3><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
                 tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
             done = true;
           }
         }
-        if (!done)
-          dirac_chain_kernel<N, CG_, CK, CW, CGMODE><<<pl.grid, CNT_G, CGm::SMEM_BYTES, st>>>(
-              tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
+        if constexpr (DFMA_GRAM) {
+          if (!done)
+            dirac_chain_kernel<N, CG_, CK, CW, CGMODE><<<pl.grid, CNT_G, CGm::SMEM_BYTES, st>>>(
+                tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
+        }
       } else
         dirac_chain_kernel<N, CG_, CK, CW, 0><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
             tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl, pe);
@@ -406,13 +413,15 @@ struct Ops {
       if (gpart != nullptr) {
         bool done = false;
         if constexpr (N % 4 == 0) {
-          if (gram_dmma()) {
+          if (gram_dmma() || !DFMA_GRAM) {
             axpy_pipe_kernel<N, APIPE_TS, 2><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
             done = true;
           }
         }
-        if (!done)
-          axpy_pipe_kernel<N, APIPE_TS, 1><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+        if constexpr (DFMA_GRAM) {
+          if (!done)
+            axpy_pipe_kernel<N, APIPE_TS, 1><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+        }
       } else {
         axpy_pipe_kernel<N, APIPE_TS, 0><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, nullptr, ctrl, pe, axpy_reverse());
       }

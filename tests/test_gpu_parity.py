@@ -143,7 +143,7 @@ def test_primitives_vs_oracle_larger(bcg, oracle, V, N):
         assert np.abs(ctx.gram(hw, hw) - np.eye(N)).max() < 1e-12
 
 
-@pytest.mark.parametrize("N", [4, 8, 12])
+@pytest.mark.parametrize("N", [4, 8, 12, 16])
 @pytest.mark.parametrize("V", [1, 2, 3, 5, 31, 47, 4737, 9475])
 def test_pipeline_kernels_ragged(bcg, oracle, V, N):
     """The warp-specialised kernels (parity-chain stencil, pipelined Q += T*M, tensor-map
