@@ -868,12 +868,30 @@ bool dmma_default() {  // read per solve, so that a test can compare both paths 
   return e ? std::atoi(e) != 0 : true;
 }
 
+bool fold_halo_default() {
+  const char* e = std::getenv("BCG_FOLD_HALO");
+  return e ? std::atoi(e) != 0 : true;
+}
+
+// Threads of the per-iteration coefficient kernels (one matrix entry per thread: N*N of them have work; a
+// barrier among fewer warps is cheaper).  BCG_STEP_THREADS overrides; read per solve.
+int step_threads(int N) {
+  const char* e = std::getenv("BCG_STEP_THREADS");
+  int t = e ? std::atoi(e) : 0;
+  if (t <= 0) t = (N * N + 31) / 32 * 32;
+  if (t < 64) t = 64;
+  if (t > kSmallThreads) t = kSmallThreads;
+  return t / 32 * 32;
+}
+
 struct LoopPlan {
   int kind;  // 0 BCG, 1 (S)BCGrQ, 2 CG / SCG (scalar coefficients, N_rhs = 1)
   int n_shifts;
   int pair;   // schedule of the multishift update: 0 plain, 1 alternating, 2 staggered (build_shift_items)
   cd* Qbuf[2];  // staggered schedule: the two Q fields ([0] holds Q of even iteration numbers, incl. the initial one)
   bool dmma;  // (S)BCGrQ update by shift_dmma_kernel (plain or paired schedule)
+  int nthr;   // threads of the coefficient kernels
+  bool fold_halo;  // the update kernel refreshes the halo of P0 itself (no halo kernel in the loop)
   cd* P0;
   cd* T;
   cd* Q;  // BCG: R
@@ -937,7 +955,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   }
   BCG_MARK(1);
   if (p.kind == 1)
-    rq_step_a_kernel<<<p.n_shifts, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
+    rq_step_a_kernel<<<p.n_shifts, p.nthr, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   else
     bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   ++*launches;
@@ -954,7 +972,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   if (r) return r;
   BCG_MARK(3);
   if (p.kind == 1)
-    rq_step_b_kernel<<<p.n_shifts, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc,
+    rq_step_b_kernel<<<p.n_shifts, p.nthr, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc,
                                                                              c->ctrl, gw1);
   else
     bcg_step_b_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc, c->ctrl,
@@ -965,7 +983,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   if (p.dmma)
     KL(c->ops->shift_update_dmma(c->stream, Qout, p.pair == 2 ? Qin : (p.pair == 1 ? fptr(c, c->work_Qp) : nullptr), &p.fp,
                                  mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1), c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0),
-                                 c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair));
+                                 c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair, p.fold_halo ? p.P0 : nullptr));
   else if (p.pair)
     KL(c->ops->shift_update_pair(c->stream, p.Q, fptr(c, c->work_Qp), &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1),
                                  c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0), c->mats + c->L.B(0, 0), c->V, c->ctrl,
@@ -974,8 +992,10 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
     KL(c->ops->shift_update(c->stream, p.Q, &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
                             p.kind == 1 ? 1 : 0, p.kind == 1 ? 0 : 1, c->ctrl, c->sms, launches));
   BCG_MARK(5);
-  r = halo_refresh(c, p.P0, 3 * c->N, c->ctrl, launches);
-  if (r) return r;
+  if (!(p.dmma && p.fold_halo)) {
+    r = halo_refresh(c, p.P0, 3 * c->N, c->ctrl, launches);
+    if (r) return r;
+  }
   BCG_MARK(6);
   return BCG_OK;
 #undef BCG_MARK
@@ -1001,6 +1021,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
   key.push_back(p.pair ? &c->work_Qp : nullptr);
   key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(p.pair)));
   key.push_back(p.dmma ? &c->work_Q : nullptr);
+  key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(p.nthr * 2 + (p.fold_halo ? 1 : 0))));
   GraphCache& g = c->graph;
   if (!g.exec || g.kind != p.kind || g.n_shifts != p.n_shifts || g.batch != batch || g.key != key) {
     if (g.exec) {
@@ -1181,6 +1202,9 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   p.kind = 1;
   p.pair = pair;
   p.dmma = dmma;
+  p.nthr = step_threads(c->N);
+  // one rank: the update kernel writes the periodic images of the first / last two sites of the new P0 itself
+  p.fold_halo = dmma && c->nranks == 1 && c->ndim == 1 && c->V >= 4 && fold_halo_default();
   p.Qbuf[0] = Q;
   p.Qbuf[1] = (pair == 2) ? fptr(c, c->work_Qp) : Q;
   p.n_shifts = n_shifts;
@@ -1246,6 +1270,7 @@ int solve_bcg(bcg_ctx* c, int x, int b, double eps, int max_it, bcg_solve_info* 
   LoopPlan p;
   std::memset(&p, 0, sizeof p);
   p.kind = 0;
+  p.nthr = kSmallThreads;
   p.n_shifts = 1;
   p.T = fptr(c, c->work_T);
   p.Q = R;
@@ -1569,7 +1594,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
           if (use_dmma)
             KL(c->ops->shift_update_dmma(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
                                          c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
-                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l, bench_sched));
+                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l, bench_sched, nullptr));
           else
             KL(c->ops->shift_update_pair(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
                                          c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
@@ -1613,7 +1638,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         if (use_dmma) {  // every system every iteration, on the tensor-instruction kernel
           KL(c->ops->shift_update_dmma(c->stream, fptr(c, h[0]), nullptr, &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
                                        c->mats + c->L.B(0), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
-                                       c->bench_ctrl, c->sms, l, 0));
+                                       c->bench_ctrl, c->sms, l, 0, nullptr));
           break;
         }
         KL(c->ops->shift_update(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),

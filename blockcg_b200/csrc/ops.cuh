@@ -61,7 +61,7 @@ struct OpsTable {
   // (build_shift_items; 2 wants Q = this iteration's Q field, Qprev = the previous iteration's).
   int (*shift_update_dmma)(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                            const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
-                           int sms, int* launches, int schedule);
+                           int sms, int* launches, int schedule, cd* p0_halo);
   int (*max_partials)(int sms);
   // sites that must be allocated after site 0 of every field / of the links (>= V + 2): the
   // tensor-map views of the chain stencil are rectangular and reach past the end of the field
@@ -529,7 +529,7 @@ struct Ops {
   template <int TSX, int NSTX>
   static int launch_dmma(cudaStream_t st, int cap, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                          const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
-                         int* launches, int paired) {
+                         int* launches, int paired, cd* p0_halo) {
     using G = ShiftDmmaGeom<N, TSX, NSTX>;
     const int grid = clamp_grid((V + TSX - 1) / TSX, cap);
     alignas(64) ShiftPairMaps maps;
@@ -547,7 +547,7 @@ struct Ops {
     }
     if (e) return e;
     shift_dmma_kernel<N, TSX, NSTX><<<grid, G::NT, G::SMEM_BYTES, st>>>(maps, Rm, A_odd, B_odd, A_even, B_even, V, ctrl,
-                                                                      paired);
+                                                                      paired, p0_halo);
     if (launches) ++*launches;
     return err();
   }
@@ -557,17 +557,17 @@ struct Ops {
   }
   static int shift_update_dmma(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                                const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
-                               int sms, int* launches, int paired) {
+                               int sms, int* launches, int paired, cd* p0_halo) {
     if constexpr (DMMA_OK) {
       prepare(sms);
       const int cfg = dmma_cfg();
       if constexpr (DMMA_CFG1)
         if (cfg == 1)
-          return launch_dmma<32, 3>(st, caps().dmma1, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired);
+          return launch_dmma<32, 3>(st, caps().dmma1, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
       if constexpr (DMMA_CFG2)
         if (cfg == 2)
-          return launch_dmma<64, 2>(st, caps().dmma2, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired);
-      return launch_dmma<SHIFT_TS, 2>(st, caps().dmma, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired);
+          return launch_dmma<64, 2>(st, caps().dmma2, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
+      return launch_dmma<SHIFT_TS, 2>(st, caps().dmma, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
     }
     return -static_cast<int>(cudaErrorNotSupported);
   }

@@ -98,7 +98,10 @@ template <int N, int TS, int NST>
 __global__ void __maxnreg__((ShiftDmmaGeom<N, TS, NST>::MAXREG))
 shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restrict__ Rrecip,
                   const cd* __restrict__ Aodd, const cd* __restrict__ Bodd, const cd* __restrict__ Aeven,
-                  const cd* __restrict__ Beven, long long V, const Ctrl* __restrict__ ctrl, int schedule) {
+                  const cd* __restrict__ Beven, long long V, const Ctrl* __restrict__ ctrl, int schedule,
+                  cd* __restrict__ p0_halo) {
+  // p0_halo != nullptr: field P of system 0 (site 0); the kernel then also writes the periodic images of its
+  // first and last two sites into the halo slots (sites V, V+1 and -2, -1), which the stencil reads next
   // Aodd/Bodd: operand slots written in odd iterations, Aeven/Beven: in even ones ([shift][N*N] each;
   // the same slots when the schedule is not paired)
   using Geo = ShiftDmmaGeom<N, TS, NST>;
@@ -223,6 +226,8 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
     cd qf[3][NTL];  // this lane's C-fragment positions of the new Q: (colour c, column 4 jt + q)
     for (int k = 0; k < n_items; ++k, ++it) {
       const int kind = s_items[k].kind;
+      const bool halo_item = p0_halo != nullptr && s_items[k].s == 0;  // new P_0: sites 0, 1 and V-2, V-1 also go to the halo slots
+      const long long xs = x0 + lsite;
       const int st = static_cast<int>(it % NS);
       mbar_wait(full + st, static_cast<uint32_t>(it / NS) & 1u);
       cd* buf = sbuf + st * STAGE;
@@ -297,7 +302,12 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
 #pragma unroll
               for (int jt = 0; jt < NTL; ++jt) {
                 const cd qq = from_prev ? myq[(c * NTL + jt) * Geo::NCT] : qf[c][jt];
-                sP[3 * (4 * jt + q) + c] = cmake(acc[jt][0] + qq.x, acc[jt][1] + qq.y);
+                const cd pn = cmake(acc[jt][0] + qq.x, acc[jt][1] + qq.y);
+                sP[3 * (4 * jt + q) + c] = pn;
+                if (halo_item) {
+                  if (xs < 2) p0_halo[(V + xs) * SITE + 3 * (4 * jt + q) + c] = pn;
+                  if (xs >= V - 2) p0_halo[(xs - V) * SITE + 3 * (4 * jt + q) + c] = pn;
+                }
               }
             }
           }
