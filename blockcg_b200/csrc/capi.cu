@@ -1204,7 +1204,8 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   p.dmma = dmma;
   p.nthr = step_threads(c->N);
   // one rank: the update kernel writes the periodic images of the first / last two sites of the new P0 itself
-  p.fold_halo = dmma && c->nranks == 1 && c->ndim == 1 && c->V >= 4 && fold_halo_default();
+  // (even V only: with an odd V the last site PAIR of a tile store reaches into halo slot V and would write its stale value back)
+  p.fold_halo = dmma && c->nranks == 1 && c->ndim == 1 && c->V >= 4 && c->V % 2 == 0 && fold_halo_default();
   p.Qbuf[0] = Q;
   p.Qbuf[1] = (pair == 2) ? fptr(c, c->work_Qp) : Q;
   p.n_shifts = n_shifts;

@@ -16,16 +16,16 @@ import blockcg_b200  # noqa: E402
 
 
 def sweep(V, N, reps, seed=0):
-    """BASELINE configs[4]: block Dirac apply / Gram / fused update at one (V, N); three fields only."""
-    rng = np.random.default_rng(seed)
-    U = rng.uniform(-1, 1, (V, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 3, 3))
+    """BASELINE configs[4]: block Dirac apply / Gram / fused update at one (V, N); three fields only, inputs
+    drawn on the device (bcg_set_links_random / bcg_field_random: a 64^4 x 32 field is 26 GB)."""
     F, Ub = 48.0 * N * V, 144.0 * V
     out = {"V": V, "N": N}
     with blockcg_b200.Context(V, N, max_shifts=1) as ctx:
-        ctx.set_links(U, 1e-3)
-        data = rng.uniform(-1, 1, (V, N, 3)) + 1j * rng.uniform(-1, 1, (V, N, 3))
-        hs = [ctx.field(data), ctx.field(data), ctx.field()]
-        del data
+        ctx.set_links_random(seed + 1, 1e-3)
+        hs = [ctx.field(), ctx.field(), ctx.field()]
+        ctx.field_random(hs[0], seed + 2)
+        ctx.field_random(hs[1], seed + 3)
+        ctx.field_random(hs[2], seed + 4)
         for name, which, nh, nbytes in [("dirac", 1, 2, 2 * F + Ub), ("dirac_gram", 0, 2, 2 * F + Ub),
                                         ("gram", 2, 2, 2 * F), ("axpy_gram", 3, 2, 3 * F),
                                         ("shift_update_S1", 4, 3, 6 * F)]:
@@ -81,7 +81,12 @@ if __name__ == "__main__":
     if a.sweep:
         for V in a.V:
             for N in a.N:
-                print(json.dumps(sweep(V, N, a.reps)), flush=True)
+                if 48.0 * N * V * 3.2 > 150e9:   # three fields must fit one GPU
+                    continue
+                try:
+                    print(json.dumps(sweep(V, N, a.reps)), flush=True)
+                except Exception as e:  # keep sweeping: one (V, N) that fails must not lose the rest
+                    print(json.dumps({"V": V, "N": N, "error": str(e)[:200]}), flush=True)
         sys.exit(0)
     for V in a.V:
         for N in a.N:
