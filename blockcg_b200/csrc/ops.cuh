@@ -201,8 +201,6 @@ struct Ops {
   using SDG2 = ShiftDmmaGeom<DMMA_N ? N : 4, 64, 2>;
   static constexpr bool DMMA_CFG1 = DMMA_OK && N <= 12 && SDG1::SMEM_BYTES <= 227 * 1024;
   static constexpr bool DMMA_CFG2 = DMMA_OK && N <= 12 && SDG2::SMEM_BYTES <= 227 * 1024;
-  using SDG3 = ShiftDmmaGeom<DMMA_N ? N : 4, 32, 2, true>;  // 3: both products in one pass over the P rows
-  static constexpr bool DMMA_CFG3 = DMMA_OK && N <= 12;
   static constexpr bool APIPE = (N % 2 == 0 && N >= 4 && N <= 12) || N == 16;  // pipelined Q += T*M (axpy_pipe.cuh)
   static constexpr bool DFMA_GRAM = N <= 12;  // GramPart (DFMA accumulators per entry) fits in registers
   static constexpr int APIPE_TS = 32;
@@ -216,7 +214,7 @@ struct Ops {
   // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
   // outside any stream capture -- and used to size the persistent grids.
   struct Caps {
-    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0, dmma = 0, dmma1 = 0, dmma2 = 0, dmma3 = 0;
+    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0, dmma = 0, dmma1 = 0, dmma2 = 0;
   };
   // Both the shared-memory opt-ins (cudaFuncSetAttribute) and the occupancy figures are per
   // DEVICE: one slot per device ordinal, filled under a lock the first time a context of that
@@ -245,10 +243,9 @@ struct Ops {
     c.shift = occupancy_blocks(shift_update_kernel<N, kNT>, kNT, SHIFT_SMEM, sms);
     if constexpr (PIPE_OK) c.pipe = occupancy_blocks(shift_pipe_kernel<N, SHIFT_TS>, SG::NT, SG::SMEM_BYTES, sms);
     if constexpr (PAIR_OK) c.pair = occupancy_blocks(shift_pair_kernel<N, SHIFT_TS>, SG::NT, SPG::SMEM_BYTES, sms);
-    if constexpr (DMMA_OK) c.dmma = occupancy_blocks(shift_dmma_kernel<N, SHIFT_TS, 2, false>, SDG::NT, SDG::SMEM_BYTES, sms);
-    if constexpr (DMMA_CFG1) c.dmma1 = occupancy_blocks(shift_dmma_kernel<N, 32, 3, false>, SDG1::NT, SDG1::SMEM_BYTES, sms);
-    if constexpr (DMMA_CFG3) c.dmma3 = occupancy_blocks(shift_dmma_kernel<N, 32, 2, true>, SDG3::NT, SDG3::SMEM_BYTES, sms);
-    if constexpr (DMMA_CFG2) c.dmma2 = occupancy_blocks(shift_dmma_kernel<N, 64, 2, false>, SDG2::NT, SDG2::SMEM_BYTES, sms);
+    if constexpr (DMMA_OK) c.dmma = occupancy_blocks(shift_dmma_kernel<N, SHIFT_TS, 2>, SDG::NT, SDG::SMEM_BYTES, sms);
+    if constexpr (DMMA_CFG1) c.dmma1 = occupancy_blocks(shift_dmma_kernel<N, 32, 3>, SDG1::NT, SDG1::SMEM_BYTES, sms);
+    if constexpr (DMMA_CFG2) c.dmma2 = occupancy_blocks(shift_dmma_kernel<N, 64, 2>, SDG2::NT, SDG2::SMEM_BYTES, sms);
     if constexpr (APIPE) {
       if constexpr (DFMA_GRAM)
         cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -529,11 +526,11 @@ struct Ops {
     return -static_cast<int>(cudaErrorNotSupported);
   }
 
-  template <int TSX, int NSTX, bool OPX = false>
+  template <int TSX, int NSTX>
   static int launch_dmma(cudaStream_t st, int cap, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                          const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
                          int* launches, int paired, cd* p0_halo) {
-    using G = ShiftDmmaGeom<N, TSX, NSTX, OPX>;
+    using G = ShiftDmmaGeom<N, TSX, NSTX>;
     const int grid = clamp_grid((V + TSX - 1) / TSX, cap);
     alignas(64) ShiftPairMaps maps;
     const long long npairs = (V + 1) / 2;
@@ -549,7 +546,7 @@ struct Ops {
       if (!e) e = make_pair_map(&maps.X[s], fp->X[s], 3 * N, G::PAIR, npairs, TSX / 2);
     }
     if (e) return e;
-    shift_dmma_kernel<N, TSX, NSTX, OPX><<<grid, G::NT, G::SMEM_BYTES, st>>>(maps, Rm, A_odd, B_odd, A_even, B_even, V, ctrl,
+    shift_dmma_kernel<N, TSX, NSTX><<<grid, G::NT, G::SMEM_BYTES, st>>>(maps, Rm, A_odd, B_odd, A_even, B_even, V, ctrl,
                                                                       paired, p0_halo);
     if (launches) ++*launches;
     return err();
@@ -570,9 +567,6 @@ struct Ops {
       if constexpr (DMMA_CFG2)
         if (cfg == 2)
           return launch_dmma<64, 2>(st, caps().dmma2, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
-      if constexpr (DMMA_CFG3)
-        if (cfg == 3)
-          return launch_dmma<32, 2, true>(st, caps().dmma3, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
       return launch_dmma<SHIFT_TS, 2>(st, caps().dmma, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
     }
     return -static_cast<int>(cudaErrorNotSupported);

@@ -36,7 +36,7 @@
 
 namespace bcg {
 
-template <int N, int TS, int NST = 2, bool ONEPASS = false>
+template <int N, int TS, int NST = 2>
 struct ShiftDmmaGeom {
   static_assert(N % 4 == 0, "the real-expanded product needs 2N a multiple of 8");
   static constexpr int NSPLIT = shift_nsplit(N), JC = N / NSPLIT;  // layout of the coefficient operands (shift_mat_index)
@@ -58,7 +58,7 @@ struct ShiftDmmaGeom {
   static constexpr size_t SMEM_BYTES = sizeof(cd) * (NSTAGE * STAGE_ELEMS + SCRATCH) + 64;
   static constexpr bool TWO_CTAS = 2 * (SMEM_BYTES + 1024) <= 227 * 1024 && NT <= 256;
   // registers are granted per thread: two CTAs of 160 threads may use up to 204 each
-  static constexpr int MAXREG = TWO_CTAS ? (ONEPASS ? 200 : 152) : (NT <= 256 ? 232 : 168);
+  static constexpr int MAXREG = TWO_CTAS ? 152 : (NT <= 256 ? 232 : 168);
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -95,10 +95,10 @@ __device__ __forceinline__ void load_coef_frags(const cd* __restrict__ sM, int l
   }
 }
 
-// ONEPASS: both coefficient matrices of an update are register-resident and every P row is read once for
-// both products (six independent accumulation chains per colour row instead of three)
-template <int N, int TS, int NST, bool ONEPASS>
-__global__ void __maxnreg__((ShiftDmmaGeom<N, TS, NST, ONEPASS>::MAXREG))
+// (Measured and dropped, profiles/r02_ab_shift_onepass_experiment.jsonl: both coefficient matrices of an update
+// register-resident, every P row read once for both products -- 180 registers, 1.39 ms per launch against 0.86.)
+template <int N, int TS, int NST>
+__global__ void __maxnreg__((ShiftDmmaGeom<N, TS, NST>::MAXREG))
 shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restrict__ Rrecip,
                   const cd* __restrict__ Aodd, const cd* __restrict__ Bodd, const cd* __restrict__ Aeven,
                   const cd* __restrict__ Beven, long long V, const Ctrl* __restrict__ ctrl, int schedule,
@@ -107,7 +107,7 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
   // first and last two sites into the halo slots (sites V, V+1 and -2, -1), which the stencil reads next
   // Aodd/Bodd: operand slots written in odd iterations, Aeven/Beven: in even ones ([shift][N*N] each;
   // the same slots when the schedule is not paired)
-  using Geo = ShiftDmmaGeom<N, TS, NST, ONEPASS>;
+  using Geo = ShiftDmmaGeom<N, TS, NST>;
   constexpr int NS = Geo::NSTAGE;
   constexpr int NCW = Geo::NCW, SITE = Geo::SITE, PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE_ELEMS;
   constexpr int NN = N * N, KS = Geo::KS, NTL = Geo::NTL;
@@ -263,43 +263,6 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
           const cd* sA = buf + 2 * TILE + 2 * u * NN;
           const cd* sB = sA + NN;
           const bool from_prev = (kind == KPREV) || (kind == KBOTH && u == 0);
-          if constexpr (ONEPASS) {
-            double fa[KS][NTL], fb[KS][NTL];
-            load_coef_frags<N>(sA, lane, fa);
-            load_coef_frags<N>(sB, lane, fb);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              double ax[NTL][2], ap[NTL][2];
-#pragma unroll
-              for (int jt = 0; jt < NTL; ++jt) ax[jt][0] = ax[jt][1] = ap[jt][0] = ap[jt][1] = 0.0;
-#pragma unroll
-              for (int js = 0; js < KS; ++js) {
-                const double a = lds_f64(dP + 2 * (6 * js + c));
-#pragma unroll
-                for (int jt = 0; jt < NTL; ++jt) {
-                  dmma_m8n8k4(ax[jt][0], ax[jt][1], a, fa[js][jt]);
-                  dmma_m8n8k4(ap[jt][0], ap[jt][1], a, fb[js][jt]);
-                }
-              }
-              if (live) {
-#pragma unroll
-                for (int jt = 0; jt < NTL; ++jt) {
-                  cd* px = sX + 3 * (4 * jt + q) + c;
-                  const cd x = *px;
-                  *px = cmake(x.x + ax[jt][0], x.y + ax[jt][1]);  // the product first, one addition into X (fields.hpp:74)
-                  const cd qq = from_prev ? myq[(c * NTL + jt) * Geo::NCT] : qf[c][jt];
-                  const cd pn = cmake(ap[jt][0] + qq.x, ap[jt][1] + qq.y);  // tmp = P * L ; tmp += Q (fields.hpp:85-86)
-                  sP[3 * (4 * jt + q) + c] = pn;
-                  if (halo_item) {
-                    if (xs < 2) p0_halo[(V + xs) * SITE + 3 * (4 * jt + q) + c] = pn;
-                    if (xs >= V - 2) p0_halo[(xs - V) * SITE + 3 * (4 * jt + q) + c] = pn;
-                  }
-                }
-              }
-            }
-            __syncwarp();
-            continue;
-          }
           double f[KS][NTL];
           // ---- X_s += P_s A : the product first, one addition into X (fields.hpp:74) ----
           load_coef_frags<N>(sA, lane, f);
