@@ -410,6 +410,7 @@ def run_ours(args, w, wname):
     # ---- part 2 (N > 1): the slab-decomposed loop against the single-domain loop, same inputs, same iterations ----
     if world > 1 and not big:
         K = args.multi_lockstep_iters
+        Xconv = [x.copy() for x in Xn[:S]] if args.max_it >= 1000000 else None   # the timed (converged) slab solutions
         solve(K)
         Xslab = [x.copy() for x in Xn[:S]]
         ho = ctx.field()
@@ -427,19 +428,37 @@ def run_ours(args, w, wname):
             sl = slice(rank * Vl, (rank + 1) * Vl)
             num = [float(np.abs(c1.download(xs1[s])[sl] - Xslab[s]).max()) for s in range(S)]
             den = [float(np.abs(c1.download(xs1[s])).max()) for s in range(S)]
+            conv = None
+            if Xconv is not None:   # ... and the CONVERGED solutions: the whole solve again on one GPU (every rank its own copy)
+                if block:
+                    i1 = c1.solve_bcgrq_dev(xs1[0], h1, w["eps"])
+                else:
+                    i1 = c1.solve_sbcgrq_dev(xs1, h1, w["shifts"], w["eps"], w["eps_shifts"])
+                cnum = [float(np.abs(c1.download(xs1[s])[sl] - Xconv[s]).max()) for s in range(S)]
+                cden = [float(np.abs(c1.download(xs1[s])).max()) for s in range(S)]
+                conv = (cnum, cden, i1.iterations)
             h2 = c1.field()
             c1.op(h2, h1, w["shifts"][0])
             o1 = c1.download(h2)
             op_num, op_den = float(np.abs(o1[sl] - op_slab).max()), float(np.abs(o1).max())
-        t = torch.tensor(num + [op_num], dtype=torch.float64, device="cuda")
+        t = torch.tensor(num + [op_num] + (conv[0] if conv else []), dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         num = t.tolist()
-        parity["multi_gpu"] = {"iterations": K, "x_rel_vs_single_domain": [n_ / d_ for n_, d_ in zip(num[:S], den)],
-                               "op_rel_vs_single_domain": num[S] / op_den, "tol": 1e-9,
-                               "note": "same inputs, %d iterations of the %d-slab loop (peer-memory exchange) against the "
-                                       "single-domain loop on one GPU; max over ranks" % (K, world)}
-        parity["multi_gpu"]["pass"] = bool(max(parity["multi_gpu"]["x_rel_vs_single_domain"]) < 1e-9 and
-                                           parity["multi_gpu"]["op_rel_vs_single_domain"] < 1e-13)
+        mg = {"lockstep_iterations": K, "lockstep_x_rel_vs_single_domain": [n_ / d_ for n_, d_ in zip(num[:S], den)],
+              "op_rel_vs_single_domain": num[S] / op_den, "tol": 1e-9,
+              "note": "same inputs: the block Dirac apply, %d iterations of the %d-slab loop (peer-memory exchange) and the "
+                      "converged solutions of the timed solve, each against the single-domain loop on one GPU; max over "
+                      "ranks.  (The Gram sums are grouped by slab, so un-converged iterates of this kappa ~ 1e7 problem "
+                      "drift apart at the rounding level and the drift is amplified until convergence -- 1e-3 after 200 "
+                      "iterations, measured -- which is why the lock-step window is short; the converged solutions agree.)"
+                      % (K, world)}
+        ok = max(mg["lockstep_x_rel_vs_single_domain"]) < 1e-9 and mg["op_rel_vs_single_domain"] < 1e-13
+        if conv:
+            mg["converged_x_rel_vs_single_domain"] = [n_ / d_ for n_, d_ in zip(num[S + 1:], conv[1])]
+            mg["iterations_slabs"], mg["iterations_single_domain"] = iters, conv[2]
+            ok = ok and max(mg["converged_x_rel_vs_single_domain"]) < 1e-9
+        mg["pass"] = bool(ok)
+        parity["multi_gpu"] = mg
 
     # ---- per-kernel roofline, measured live with CUDA events on same-size fields ----
     peaks = {}
@@ -617,7 +636,7 @@ def main():
                     help="iterations of the last warm-up solve timed stage by stage inside the loop (0: off)")
     ap.add_argument("--profile-after", type=int, default=3000,
                     help="iterations to run before the profiled window starts (sustained clocks)")
-    ap.add_argument("--multi-lockstep-iters", type=int, default=200,
+    ap.add_argument("--multi-lockstep-iters", type=int, default=8,
                     help="N > 1 GPUs: iterations of the slab loop compared with the single-domain loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL halo / all-reduce instead of peer-memory stores")
