@@ -54,6 +54,8 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   using Geo = AxpyPipeGeom<N, TS>;
   constexpr int NSPLIT = Geo::NSPLIT, JC = Geo::JC, SPW = Geo::SPW, NCW = Geo::NCW, SITE = Geo::SITE;
   constexpr int PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE, NS = Geo::NSTAGE;
+  pdl_wait();
+  pdl_trigger();
   if (ctrl != nullptr && ctrl->done) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -269,7 +269,7 @@ int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
   if (c->nranks == 1) {
     const long long n = 2 * c->halo * site;
     const unsigned blocks = static_cast<unsigned>(n / 256 + 1 < 2048 ? n / 256 + 1 : 2048);
-    halo_wrap_kernel<<<blocks, 256, 0, c->stream>>>(f, c->V, site, c->halo, ctrl);
+    launch_pdl(halo_wrap_kernel, blocks, 256, 0, c->stream, f, c->V, site, c->halo, ctrl);
     if (launches) ++*launches;
     CU(cudaGetLastError());
     return BCG_OK;
@@ -279,8 +279,8 @@ int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
     // inside the iteration loop: boundary sites go straight into the neighbours' buffers over
     // NVLink (P2P stores + sequence word), the receiver copies them into its halo slots
     const HaloPeers hp = halo_peers(c);
-    halo_push_kernel<<<1, 128, 0, c->stream>>>(f, c->V, site, hp, ctrl);
-    halo_wait_unpack_kernel<<<1, 128, 0, c->stream>>>(f, c->V, site, hp, const_cast<Ctrl*>(ctrl));
+    launch_pdl(halo_push_kernel, 1, 128, 0, c->stream, f, c->V, site, hp, ctrl);
+    launch_pdl(halo_wait_unpack_kernel, 1, 128, 0, c->stream, f, c->V, site, hp, const_cast<Ctrl*>(ctrl));
     if (launches) *launches += 2;
     CU(cudaGetLastError());
     return BCG_OK;
@@ -955,7 +955,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   }
   BCG_MARK(1);
   if (p.kind == 1)
-    rq_step_a_kernel<<<p.n_shifts, p.nthr, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
+    launch_pdl(rq_step_a_kernel, p.n_shifts, p.nthr, c->small_smem, c->stream, c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   else
     bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   ++*launches;
@@ -972,8 +972,8 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   if (r) return r;
   BCG_MARK(3);
   if (p.kind == 1)
-    rq_step_b_kernel<<<p.n_shifts, p.nthr, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc,
-                                                                             c->ctrl, gw1);
+    launch_pdl(rq_step_b_kernel, p.n_shifts, p.nthr, c->small_smem, c->stream, c->mats, c->L, c->b_norm, gsrc, nsrc, c->ctrl,
+               gw1);
   else
     bcg_step_b_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, c->b_norm, gsrc, nsrc, c->ctrl,
                                                                       gw1);

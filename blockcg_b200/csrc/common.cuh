@@ -3,8 +3,31 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
+#include <utility>
 
 namespace bcg {
+
+// BCG_PDL=0 launches the loop's kernels with plain stream order (read per launch: A/B runs in one process)
+inline bool pdl_enabled() {
+  const char* e = std::getenv("BCG_PDL");
+  return e ? std::atoi(e) != 0 : true;
+}
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic stream-serialization attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 typedef double2 cd;  // complex128: x = re, y = im
 
@@ -218,6 +241,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+
+// ---- programmatic dependent launch (griddepcontrol) --------------------------------------------
+// Every kernel of the iteration loop starts with pdl_wait(): when it was launched with the programmatic
+// stream-serialization attribute its CTAs may become resident -- and run their prologue (barrier
+// initialisation, descriptor fetches) -- while the previous kernel of the stream is still draining; the wait
+// returns once that kernel has completed and its memory is visible.  Launched normally it is a no-op.
+// pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as this grid's CTAs have all started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- mbarrier + 1-D bulk TMA (cp.async.bulk) ------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

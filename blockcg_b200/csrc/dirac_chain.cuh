@@ -334,6 +334,8 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   constexpr int WARP_STORE = WARP_LOAD + 1;
   constexpr int R = Geo::R, SITE = Geo::SITE, PP = Geo::PP, PU = Geo::PU;
   constexpr int SP = Geo::SP, SU = Geo::SU, SO = Geo::SO;
+  pdl_wait();
+  pdl_trigger();
   if (ctrl != nullptr && (ctrl->done | ctrl->stop)) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -881,6 +881,8 @@ static __global__ void fill_uniform_kernel(double* __restrict__ dst, long long n
 // chain, one x3-slice for the 4-D operator.
 static __global__ void halo_wrap_kernel(cd* __restrict__ f, long long V, int site, long long H,
                                         const Ctrl* __restrict__ ctrl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctrl != nullptr && ctrl->done) return;
   const long long n = 2 * H * site;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -898,6 +900,8 @@ static __global__ void halo_wrap_kernel(cd* __restrict__ f, long long V, int sit
 // that follows iteration i: seq_base + i (i = 0: the refresh before the loop).
 static __global__ void halo_push_kernel(const cd* __restrict__ f, long long V, int site, HaloPeers hp,
                                         const Ctrl* __restrict__ ctrl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctrl->done) return;
   const unsigned long long k = ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter);
   const int n = 2 * site;
@@ -916,6 +920,8 @@ static __global__ void halo_push_kernel(const cd* __restrict__ f, long long V, i
 }
 static __global__ void halo_wait_unpack_kernel(cd* __restrict__ f, long long V, int site, HaloPeers hp,
                                                Ctrl* __restrict__ ctrl) {
+  pdl_wait();
+  pdl_trigger();
   if (ctrl->done) return;
   const unsigned long long k = ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter);
   __shared__ int timed_out;

@@ -352,19 +352,19 @@ struct Ops {
         bool done = false;
         if constexpr (N % 4 == 0 && CK == 16) {
           if (gram_dmma() || !DFMA_GRAM) {
-            dirac_chain_kernel<N, CG_, CK, CW, 3><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
-                tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
+            launch_pdl(dirac_chain_kernel<N, CG_, CK, CW, 3>, pl.grid, CGm::NT, CGm::SMEM_BYTES, st, tmP, tmO, tmU, in, U, V,
+                       pl.L, m2, sigma, gpart, ctrl, pe);
             done = true;
           }
         }
         if constexpr (DFMA_GRAM) {
           if (!done)
-            dirac_chain_kernel<N, CG_, CK, CW, CGMODE><<<pl.grid, CNT_G, CGm::SMEM_BYTES, st>>>(
-                tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, gpart, ctrl, pe);
+            launch_pdl(dirac_chain_kernel<N, CG_, CK, CW, CGMODE>, pl.grid, CNT_G, CGm::SMEM_BYTES, st, tmP, tmO, tmU, in, U,
+                       V, pl.L, m2, sigma, gpart, ctrl, pe);
         }
       } else
-        dirac_chain_kernel<N, CG_, CK, CW, 0><<<pl.grid, CGm::NT, CGm::SMEM_BYTES, st>>>(
-            tmP, tmO, tmU, in, U, V, pl.L, m2, sigma, nullptr, ctrl, pe);
+        launch_pdl(dirac_chain_kernel<N, CG_, CK, CW, 0>, pl.grid, CGm::NT, CGm::SMEM_BYTES, st, tmP, tmO, tmU, in, U, V, pl.L,
+                   m2, sigma, static_cast<cd*>(nullptr), ctrl, pe);
       if (launches) ++*launches;
       e = err();
       return e ? e : (gpart != nullptr ? 1 : 0);  // the kernel leaves the fully reduced block in gpart[0]
@@ -414,16 +414,16 @@ struct Ops {
         bool done = false;
         if constexpr (N % 4 == 0) {
           if (gram_dmma() || !DFMA_GRAM) {
-            axpy_pipe_kernel<N, APIPE_TS, 2><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+            launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 2>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
             done = true;
           }
         }
         if constexpr (DFMA_GRAM) {
           if (!done)
-            axpy_pipe_kernel<N, APIPE_TS, 1><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+            launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 1>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
         }
       } else {
-        axpy_pipe_kernel<N, APIPE_TS, 0><<<grid, APG::NT, APG::SMEM_BYTES, st>>>(tmQ, tmQo, tmT, M, V, nullptr, ctrl, pe, axpy_reverse());
+        launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 0>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, static_cast<cd*>(nullptr), ctrl, pe, axpy_reverse());
       }
       if (launches) ++*launches;
       e = err();
@@ -546,8 +546,8 @@ struct Ops {
       if (!e) e = make_pair_map(&maps.X[s], fp->X[s], 3 * N, G::PAIR, npairs, TSX / 2);
     }
     if (e) return e;
-    shift_dmma_kernel<N, TSX, NSTX><<<grid, G::NT, G::SMEM_BYTES, st>>>(maps, Rm, A_odd, B_odd, A_even, B_even, V, ctrl,
-                                                                      paired, p0_halo);
+    launch_pdl(shift_dmma_kernel<N, TSX, NSTX>, grid, G::NT, G::SMEM_BYTES, st, maps, Rm, A_odd, B_odd, A_even, B_even, V, ctrl,
+               paired, p0_halo);
     if (launches) ++*launches;
     return err();
   }

@@ -111,6 +111,8 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
   constexpr int NS = Geo::NSTAGE;
   constexpr int NCW = Geo::NCW, SITE = Geo::SITE, PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE_ELEMS;
   constexpr int NN = N * N, KS = Geo::KS, NTL = Geo::NTL;
+  pdl_wait();
+  pdl_trigger();
   if (ctrl->done) return;
   const int iter = ctrl->iter;
   const bool odd = (iter & 1) != 0;

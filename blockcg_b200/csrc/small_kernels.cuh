@@ -594,6 +594,8 @@ rq_init_kernel(cd* __restrict__ mats, MatLayout L, double* __restrict__ b_norm, 
 __global__ void __launch_bounds__(kSmallThreads)
 rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpart, int nparts,
                  Ctrl* __restrict__ ctrl, const GramWait gw) {
+  pdl_wait();
+  pdl_trigger();
   if (ctrl->done) return;
   if (ctrl->stop) {
     __syncthreads();
@@ -689,6 +691,8 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
 __global__ void __launch_bounds__(kSmallThreads)
 rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ b_norm,
                  const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl, const GramWait gw) {
+  pdl_wait();
+  pdl_trigger();
   if (ctrl->done) return;
   const int sh = blockIdx.x;
   if (sh >= ctrl->n_unconv) return;
