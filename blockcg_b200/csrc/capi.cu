@@ -341,11 +341,11 @@ int gram_to_gred(bcg_ctx* c, const cd* a, const cd* b, int* launches) {
 // 1-D chain: one fused kernel.  4-D: two sweeps through the intermediate field (whose halo is
 // refreshed in between) and the stand-alone Gram kernel.
 int apply_op(bcg_ctx* c, cd* in, cd* out, double sigma, bool want_gram, const Ctrl* ctrl, int* launches,
-             const GramPeers* peers, int* np_out) {
+             const GramPeers* peers, int* np_out, const HaloFold* hf = nullptr) {
   const double m2 = c->mass * c->mass;
   if (c->ndim == 1) {
     int np = c->ops->dirac(c->stream, in, out, uptr(c), c->V, m2, sigma, want_gram ? c->gpart : nullptr, ctrl, c->sms,
-                           launches, peers);
+                           launches, peers, hf);
     KL(np);
     *np_out = np;
     return BCG_OK;
@@ -915,7 +915,15 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   const GramPeers gp0 = fused ? gram_peers(c, 0) : GramPeers{}, gp1 = fused ? gram_peers(c, 1) : GramPeers{};
   const GramWait gw0 = fused ? gram_wait(c, 0) : GramWait{}, gw1 = fused ? gram_wait(c, 1) : GramWait{};
   int np = 0;
-  int r = apply_op(c, p.P0, p.T, p.sigma0, true, c->ctrl, launches, fused ? &gp0 : nullptr, &np);
+  // slab decomposition: the halo exchange of P_0 is folded into the update kernel (push) and the stencil (wait + unpack)
+  HaloFold hf;
+  std::memset(&hf, 0, sizeof hf);
+  const bool fold_mg = p.fold_halo && c->nranks > 1;
+  if (fold_mg) {
+    hf.hp = halo_peers(c);
+    hf.on = 1;
+  }
+  int r = apply_op(c, p.P0, p.T, p.sigma0, true, c->ctrl, launches, fused ? &gp0 : nullptr, &np, fold_mg ? &hf : nullptr);
   if (r) return r;
   r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
@@ -983,7 +991,8 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   if (p.dmma)
     KL(c->ops->shift_update_dmma(c->stream, Qout, p.pair == 2 ? Qin : (p.pair == 1 ? fptr(c, c->work_Qp) : nullptr), &p.fp,
                                  mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1), c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0),
-                                 c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair, p.fold_halo ? p.P0 : nullptr));
+                                 c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair,
+                                 (p.fold_halo && c->nranks == 1) ? p.P0 : nullptr, fold_mg ? &hf : nullptr));
   else if (p.pair)
     KL(c->ops->shift_update_pair(c->stream, p.Q, fptr(c, c->work_Qp), &p.fp, mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1),
                                  c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0), c->mats + c->L.B(0, 0), c->V, c->ctrl,
@@ -1205,7 +1214,10 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   p.nthr = step_threads(c->N);
   // one rank: the update kernel writes the periodic images of the first / last two sites of the new P0 itself
   // (even V only: with an odd V the last site PAIR of a tile store reaches into halo slot V and would write its stale value back)
-  p.fold_halo = dmma && c->nranks == 1 && c->ndim == 1 && c->V >= 4 && c->V % 2 == 0 && fold_halo_default();
+  // Several ranks with mapped peer buffers: the update kernel stores the boundary sites into the neighbours' buffers
+  // and the next stencil waits for them and unpacks them itself (needs the parity-chain stencil: N = 4, 8, 12, 16).
+  p.fold_halo = dmma && c->ndim == 1 && c->V >= 4 && c->V % 2 == 0 && fold_halo_default() &&
+                (c->nranks == 1 || (c->p2p_ready && c->ops->fused_exchange));
   p.Qbuf[0] = Q;
   p.Qbuf[1] = (pair == 2) ? fptr(c, c->work_Qp) : Q;
   p.n_shifts = n_shifts;
@@ -1595,7 +1607,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
           if (use_dmma)
             KL(c->ops->shift_update_dmma(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
                                          c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
-                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l, bench_sched, nullptr));
+                                         c->mats + Lp.B(0, 0), c->V, c->bench_ctrl + i, c->sms, l, bench_sched, nullptr, nullptr));
           else
             KL(c->ops->shift_update_pair(c->stream, fptr(c, h[0]), fptr(c, c->work_Qp), &fp, mat(c, M_SCRATCH),
                                          c->mats + Lp.A(0, 1), c->mats + Lp.B(0, 1), c->mats + Lp.A(0, 0),
@@ -1639,7 +1651,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
         if (use_dmma) {  // every system every iteration, on the tensor-instruction kernel
           KL(c->ops->shift_update_dmma(c->stream, fptr(c, h[0]), nullptr, &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),
                                        c->mats + c->L.B(0), c->mats + c->L.A(0), c->mats + c->L.B(0), c->V,
-                                       c->bench_ctrl, c->sms, l, 0, nullptr));
+                                       c->bench_ctrl, c->sms, l, 0, nullptr, nullptr));
           break;
         }
         KL(c->ops->shift_update(c->stream, fptr(c, h[0]), &fp, mat(c, M_SCRATCH), c->mats + c->L.A(0),

@@ -230,6 +230,14 @@ struct HaloPeers {
   const unsigned long long* my_seq_lo;
   const unsigned long long* my_seq_hi;
 };
+// Slab decomposition with the halo exchange folded into the kernels that produce / consume it: the update
+// kernel stores the first and last two sites of the new P_0 straight into the neighbours' buffers and
+// publishes the sequence number; the stencil of the next iteration waits for its neighbours' and copies
+// them into the halo slots of the field in its prologue -- no halo kernel in the loop.
+struct HaloFold {
+  HaloPeers hp;
+  int on;
+};
 struct GramWait {                       // consumer side of a Gram channel
   const cd* slots;                      // this rank's block area: [2 parities][nranks][N*N]
   const unsigned long long* seq;        // this rank's sequence words: [nranks]

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__((GMODE == 2 ? (ChainGeom<N, G, K, W>::NSW + 2)
 dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmU, const cd* __restrict__ in,
                    const cd* __restrict__ U, long long V, long long L, double m2, double sigma,
-                   cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl, const GramPeers peers) {
+                   cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl, const GramPeers peers, const HaloFold hf) {
   using Geo = ChainGeom<N, G, K, W>;
   constexpr int WARP_LOAD = (GMODE == 2) ? Geo::NSW : Geo::WARP_LOAD;
   constexpr int WARP_STORE = WARP_LOAD + 1;
@@ -359,6 +359,47 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
   const int T = static_cast<int>(L / W);                      // tiles
   const long long chain0 = static_cast<long long>(blockIdx.x) * K;  // first sub-chain of this CTA
+  // ---- folded halo exchange (slab decomposition): wait for the neighbours' boundary sites of this P ----
+  const cd* lo_src = nullptr;  // sites -2, -1 as the left neighbour stored them (read by the chain start of chain 0)
+  if (hf.on && ctrl != nullptr) {
+    const unsigned long long kseq = ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter);
+    const int hn = 2 * SITE;
+    // sites this CTA reads: its chains' starts (generic loads) and windows 0 .. T of chains chain0 .. chain0 + K (TMA)
+    const bool need_lo = chain0 == 0;
+    const bool need_hi = chain0 * L <= V + 1 && (chain0 + K + 1) * L + W > V;
+    if (need_lo || need_hi) {
+      __shared__ int halo_timed_out;
+      if (tid == 0) halo_timed_out = 0;
+      __syncthreads();
+      if ((tid == 0 && need_lo) || (tid == 1 && need_hi)) {
+        const unsigned long long* wseq = tid ? hf.hp.my_seq_hi : hf.hp.my_seq_lo;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(wseq) < kseq)
+          if (clock64() - t0 > kSpinTimeoutClocks) {
+            halo_timed_out = 1;
+            break;
+          }
+      }
+      __syncthreads();
+      if (halo_timed_out) {
+        if (tid == 0) {
+          Ctrl* cw = const_cast<Ctrl*>(ctrl);
+          cw->status = 4;
+          cw->done = 1;
+        }
+        return;
+      }
+      if (need_hi) {  // slots V, V+1 are read through the tensor map: they must be in the field itself
+        cd* fw = const_cast<cd*>(in);
+        const cd* hi = hf.hp.my_hi + (kseq & 1ull) * hn;
+        for (int i = tid; i < hn; i += blockDim.x) fw[V * SITE + i] = __ldcg(reinterpret_cast<const double2*>(hi + i));
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> visible to the tensor copies below
+      }
+      __syncthreads();
+    }
+    lo_src = hf.hp.my_lo + (kseq & 1ull) * hn;
+  }
   // sub-chain q covers out sites [q*L, min((q+1)*L, V))
   auto chain_start = [&](int k) { return (chain0 + k) * L; };
   auto chain_end = [&](int k) {
@@ -519,7 +560,15 @@ dirac_chain_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         for (int c = 0; c < 3; ++c) acc[r][c] = czero();
       load_cols<N, R>(in + x * SITE + col0, v);
       apply_link<R>(U + (x - 1) * 9, v, acc);
-      load_cols<N, R>(in + (x - 2) * SITE + col0, v);
+      if (lo_src != nullptr && x < 2) {  // sites -2, -1: straight from the communication buffer (written by the peer)
+        const cd* src = lo_src + x * SITE + col0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[r][c] = __ldcg(reinterpret_cast<const double2*>(src + r * 3 + c));
+      } else {
+        load_cols<N, R>(in + (x - 2) * SITE + col0, v);
+      }
       apply_link_dag_sub<R>(U + (x - 2) * 9, v, acc);
 #pragma unroll
       for (int r = 0; r < R; ++r)

@@ -22,7 +22,7 @@ struct OpsTable {
   // or a negative cudaError_t.
   // peers: peer-memory targets of the fused Gram exchange (nullptr = none)
   int (*dirac)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
-               cd* gpart, const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers);
+               cd* gpart, const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers, const HaloFold* hf);
   // first-generation tile kernel (intermediate staged in shared memory), kept for comparison
   int (*dirac_v1)(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
                   cd* gpart, const Ctrl* ctrl, int sms, int* launches);
@@ -61,7 +61,7 @@ struct OpsTable {
   // (build_shift_items; 2 wants Q = this iteration's Q field, Qprev = the previous iteration's).
   int (*shift_update_dmma)(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                            const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
-                           int sms, int* launches, int schedule, cd* p0_halo);
+                           int sms, int* launches, int schedule, cd* p0_halo, const HaloFold* hf);
   int (*max_partials)(int sms);
   // sites that must be allocated after site 0 of every field / of the links (>= V + 2): the
   // tensor-map views of the chain stencil are rectangular and reach past the end of the field
@@ -336,9 +336,11 @@ struct Ops {
   }
 
   static int dirac(cudaStream_t st, const cd* in, cd* out, const cd* U, long long V, double m2, double sigma,
-                   cd* gpart, const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers) {
+                   cd* gpart, const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers, const HaloFold* hfp) {
     GramPeers pe;
     if (peers) pe = *peers; else std::memset(&pe, 0, sizeof pe);
+    HaloFold hf;
+    if (hfp) hf = *hfp; else std::memset(&hf, 0, sizeof hf);
     if (force_v1() & 1) return dirac_v1(st, in, out, U, V, m2, sigma, gpart, ctrl, sms, launches);
     if constexpr (CHAIN) {
       prepare(sms);
@@ -353,18 +355,18 @@ struct Ops {
         if constexpr (N % 4 == 0 && CK == 16) {
           if (gram_dmma() || !DFMA_GRAM) {
             launch_pdl(dirac_chain_kernel<N, CG_, CK, CW, 3>, pl.grid, CGm::NT, CGm::SMEM_BYTES, st, tmP, tmO, tmU, in, U, V,
-                       pl.L, m2, sigma, gpart, ctrl, pe);
+                       pl.L, m2, sigma, gpart, ctrl, pe, hf);
             done = true;
           }
         }
         if constexpr (DFMA_GRAM) {
           if (!done)
             launch_pdl(dirac_chain_kernel<N, CG_, CK, CW, CGMODE>, pl.grid, CNT_G, CGm::SMEM_BYTES, st, tmP, tmO, tmU, in, U,
-                       V, pl.L, m2, sigma, gpart, ctrl, pe);
+                       V, pl.L, m2, sigma, gpart, ctrl, pe, hf);
         }
       } else
         launch_pdl(dirac_chain_kernel<N, CG_, CK, CW, 0>, pl.grid, CGm::NT, CGm::SMEM_BYTES, st, tmP, tmO, tmU, in, U, V, pl.L,
-                   m2, sigma, static_cast<cd*>(nullptr), ctrl, pe);
+                   m2, sigma, static_cast<cd*>(nullptr), ctrl, pe, hf);
       if (launches) ++*launches;
       e = err();
       return e ? e : (gpart != nullptr ? 1 : 0);  // the kernel leaves the fully reduced block in gpart[0]
@@ -529,8 +531,10 @@ struct Ops {
   template <int TSX, int NSTX>
   static int launch_dmma(cudaStream_t st, int cap, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                          const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
-                         int* launches, int paired, cd* p0_halo) {
+                         int* launches, int paired, cd* p0_halo, const HaloFold* hfp) {
     using G = ShiftDmmaGeom<N, TSX, NSTX>;
+    HaloFold hf;
+    if (hfp) hf = *hfp; else std::memset(&hf, 0, sizeof hf);
     const int grid = clamp_grid((V + TSX - 1) / TSX, cap);
     alignas(64) ShiftPairMaps maps;
     const long long npairs = (V + 1) / 2;
@@ -547,7 +551,7 @@ struct Ops {
     }
     if (e) return e;
     launch_pdl(shift_dmma_kernel<N, TSX, NSTX>, grid, G::NT, G::SMEM_BYTES, st, maps, Rm, A_odd, B_odd, A_even, B_even, V, ctrl,
-               paired, p0_halo);
+               paired, p0_halo, hf);
     if (launches) ++*launches;
     return err();
   }
@@ -557,17 +561,17 @@ struct Ops {
   }
   static int shift_update_dmma(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                                const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
-                               int sms, int* launches, int paired, cd* p0_halo) {
+                               int sms, int* launches, int paired, cd* p0_halo, const HaloFold* hfp) {
     if constexpr (DMMA_OK) {
       prepare(sms);
       const int cfg = dmma_cfg();
       if constexpr (DMMA_CFG1)
         if (cfg == 1)
-          return launch_dmma<32, 3>(st, caps().dmma1, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
+          return launch_dmma<32, 3>(st, caps().dmma1, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo, hfp);
       if constexpr (DMMA_CFG2)
         if (cfg == 2)
-          return launch_dmma<64, 2>(st, caps().dmma2, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
-      return launch_dmma<SHIFT_TS, 2>(st, caps().dmma, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo);
+          return launch_dmma<64, 2>(st, caps().dmma2, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo, hfp);
+      return launch_dmma<SHIFT_TS, 2>(st, caps().dmma, Q, Qprev, fp, Rm, A_odd, B_odd, A_even, B_even, V, ctrl, launches, paired, p0_halo, hfp);
     }
     return -static_cast<int>(cudaErrorNotSupported);
   }

@@ -102,7 +102,7 @@ __global__ void __maxnreg__((ShiftDmmaGeom<N, TS, NST>::MAXREG))
 shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restrict__ Rrecip,
                   const cd* __restrict__ Aodd, const cd* __restrict__ Bodd, const cd* __restrict__ Aeven,
                   const cd* __restrict__ Beven, long long V, const Ctrl* __restrict__ ctrl, int schedule,
-                  cd* __restrict__ p0_halo) {
+                  cd* __restrict__ p0_halo, const HaloFold hf) {
   // p0_halo != nullptr: field P of system 0 (site 0); the kernel then also writes the periodic images of its
   // first and last two sites into the halo slots (sites V, V+1 and -2, -1), which the stencil reads next
   // Aodd/Bodd: operand slots written in odd iterations, Aeven/Beven: in even ones ([shift][N*N] each;
@@ -232,6 +232,11 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
     for (int k = 0; k < n_items; ++k, ++it) {
       const int kind = s_items[k].kind;
       const bool halo_item = p0_halo != nullptr && s_items[k].s == 0;  // new P_0: sites 0, 1 and V-2, V-1 also go to the halo slots
+      // slab decomposition: ... or straight into the neighbours' buffers (P2P stores over NVLink), published below
+      const bool push_item = hf.on && s_items[k].s == 0;
+      const unsigned long long kseq = ctrl->seq_base + static_cast<unsigned long long>(iter);
+      cd* to_left = hf.hp.hi_of_left + (kseq & 1ull) * (2 * SITE);    // my sites 0, 1     -> left neighbour's slots V, V+1
+      cd* to_right = hf.hp.lo_of_right + (kseq & 1ull) * (2 * SITE);  // my sites V-2, V-1 -> right neighbour's slots -2, -1
       const long long xs = x0 + lsite;
       const int st = static_cast<int>(it % NS);
       mbar_wait(full + st, static_cast<uint32_t>(it / NS) & 1u);
@@ -313,10 +318,28 @@ shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restri
                   if (xs < 2) p0_halo[(V + xs) * SITE + 3 * (4 * jt + q) + c] = pn;
                   if (xs >= V - 2) p0_halo[(xs - V) * SITE + 3 * (4 * jt + q) + c] = pn;
                 }
+                if (push_item) {
+                  if (xs < 2) to_left[xs * SITE + 3 * (4 * jt + q) + c] = pn;
+                  if (xs >= V - 2) to_right[(xs - (V - 2)) * SITE + 3 * (4 * jt + q) + c] = pn;
+                }
               }
             }
           }
           __syncwarp();  // the new rows are complete before the second update reads them
+          if (push_item) {
+            // both boundary sites of a side sit in one warp (V even, tiles and warps hold whole site pairs): the stores
+            // of its lanes are fenced at system scope, then one lane publishes the iteration's sequence number
+            const bool has_lo = x0 == 0 && warp == 0;
+            const bool has_hi = V - 2 >= x0 && V - 2 < x0 + TS && warp == static_cast<int>((V - 2 - x0) / Geo::SPW);
+            if (has_lo || has_hi) {
+              __threadfence_system();
+              __syncwarp();
+              if (lane == 0) {
+                if (has_lo) st_release_sys(hf.hp.seq_hi_of_left, kseq);
+                if (has_hi) st_release_sys(hf.hp.seq_lo_of_right, kseq);
+              }
+            }
+          }
         }
       }
       fence_proxy_async();
