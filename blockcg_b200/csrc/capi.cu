@@ -879,7 +879,7 @@ int step_threads(int N) {
   const char* e = std::getenv("BCG_STEP_THREADS");
   int t = e ? std::atoi(e) : 0;
   if (t <= 0) t = (N * N + 31) / 32 * 32;
-  if (t < 64) t = 64;
+  if (t < 32) t = 32;
   if (t > kSmallThreads) t = kSmallThreads;
   return t / 32 * 32;
 }
