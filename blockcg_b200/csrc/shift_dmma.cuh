@@ -96,7 +96,10 @@ __device__ __forceinline__ void load_coef_frags(const cd* __restrict__ sM, int l
 }
 
 // (Measured and dropped, profiles/r02_ab_shift_onepass_experiment.jsonl: both coefficient matrices of an update
-// register-resident, every P row read once for both products -- 180 registers, 1.39 ms per launch against 0.86.)
+// register-resident, every P row read once for both products -- 180 registers, 1.39 ms per launch against 0.86;
+// profiles/r02_ab_shift_chain_scheduling_experiment.jsonl: tensor instructions not `volatile`, or all three colour
+// rows of a product in flight at once (nine accumulation chains) -- no gain: the accumulation chains are not what
+// the kernel waits for.)
 template <int N, int TS, int NST>
 __global__ void __maxnreg__((ShiftDmmaGeom<N, TS, NST>::MAXREG))
 shift_dmma_kernel(const __grid_constant__ ShiftPairMaps maps, const cd* __restrict__ Rrecip,
