@@ -460,6 +460,39 @@ def run_ours(args, w, wname):
         mg["pass"] = bool(ok)
         parity["multi_gpu"] = mg
 
+    # ---- weak-scaling probe: the same sites PER GPU as the 1-GPU headline run, capped iterations (extra key) ----
+    weak = None
+    if args.weak_iters > 0 and not big and w["solver"] == "sbcgrq":
+        Vw = V   # per GPU; the global chain has world * V sites, inputs drawn on the device (counter-based generator)
+        cw = blockcg_b200.Context(Vw, N, max_shifts=S, device=local, rank=rank, nranks=world)
+        try:
+            if world > 1:
+                uid = torch.zeros(blockcg_b200.capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    uid.copy_(torch.frombuffer(bytearray(cw.unique_id()), dtype=torch.uint8))
+                dist.broadcast(uid, 0)
+                cw.comm_init(bytes(uid.cpu().numpy().tobytes()))
+                if not args.no_p2p:
+                    from blockcg_b200.distributed import exchange_ipc_handles
+                    exchange_ipc_handles(dist, cw, torch.device("cuda", local))
+            cw.set_links_random(7, w["mass"])
+            hbw = cw.field()
+            cw.field_random(hbw, 8)
+            xsw = [cw.field() for _ in range(S)]
+            cw.solve_sbcgrq_dev(xsw, hbw, w["shifts"], w["eps"], w["eps_shifts"], args.weak_iters)   # warm-up (graph capture)
+            barrier()
+            iw = cw.solve_sbcgrq_dev(xsw, hbw, w["shifts"], w["eps"], w["eps_shifts"], args.weak_iters)
+            tw = torch.tensor([iw.solve_ms], dtype=torch.float64, device="cuda")
+            if dist is not None:
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            weak = {"sites_per_gpu": Vw, "global_sites": Vw * world, "iterations": iw.iterations,
+                    "ms_per_iteration": float(tw.item()) / max(iw.iterations, 1),
+                    "note": "weak scaling: the headline volume PER GPU (global chain of n_gpus x that), device-generated inputs, "
+                            "first %d iterations (all %d systems active), max over ranks; compare ms_per_iteration across n_gpus"
+                            % (args.weak_iters, S)}
+        finally:
+            cw.close()
+
     # ---- per-kernel roofline, measured live with CUDA events on same-size fields ----
     peaks = {}
     try:
@@ -600,7 +633,8 @@ def run_ours(args, w, wname):
             "timed_region_s_per_step": region_s,
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(F) * world,
                     "d2h_bytes_per_step": int(S * F) * world},
-            "gpu_launches": launches, "clocks": clocks, "parity": parity, "loop": loop, "roofline": roofline,
+            "gpu_launches": launches, "clocks": clocks, "parity": parity, "loop": loop, "weak_scaling": weak,
+            "roofline": roofline,
             "dirac_op": {"kernel": "dirac_chain_kernel (block Dirac apply; +gram = with the fused P^dag T epilogue)",
                          "GBps": kern["dirac"]["achieved"], "frac_of_hbm_peak": kern["dirac"]["frac"],
                          "ms": kern["dirac"]["ms"], "GBps_with_gram": dirac["achieved"],
@@ -638,6 +672,8 @@ def main():
                     help="iterations to run before the profiled window starts (sustained clocks)")
     ap.add_argument("--multi-lockstep-iters", type=int, default=8,
                     help="N > 1 GPUs: iterations of the slab loop compared with the single-domain loop")
+    ap.add_argument("--weak-iters", type=int, default=200,
+                    help="iterations of the weak-scaling probe (the headline volume per GPU; 0: off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL halo / all-reduce instead of peer-memory stores")
     ap.add_argument("--record-iterations", action="store_true")
