@@ -511,7 +511,8 @@ def run_ours(args, w, wname):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(wname, {}) if world == 1 else {}
     except Exception:
         pass
-    paired = S > 1 and os.environ.get("BCG_PAIR", "1") != "0"
+    sched, depth = (stats["schedule"], stats["depth"]) if S > 1 else (0, 1)  # what the timed solve ran (capi.cu: pair_default)
+    paired = sched != 0
 
     def bench(name, which, nh, ns, nbytes, per_rep=1, reps=20):
         ms, _ = ctx.bench_kernel(which, max(reps // per_rep, 2), hs[:nh], ns)
@@ -528,10 +529,14 @@ def run_ours(args, w, wname):
     # second iteration, shift_pair.cuh); "shift_update[a]" the plain kernel (every system every iteration).
     dmma = os.environ.get("BCG_DMMA", "1") != "0" and N % 4 == 0   # shift_dmma.cuh: the same update on the FP64 tensor instruction
     upd = ("shift_dmma_pair" if paired else "shift_dmma") if dmma else ("shift_pair" if paired else "shift_update")
+    if sched == 3:
+        upd = "shift_stag%d" % depth   # shift_stag.cuh: the shifted systems every depth-th iteration
     plain = "shift_dmma" if dmma else "shift_update"
     t_upd = {}
     for a in range(1, S + 1):
-        if paired:
+        if sched == 3:   # one repetition = `depth` consecutive launches (every group of systems served once)
+            t_upd[a] = bench("%s[%d]" % (upd, a), 14, 1 + 2 * a, a, (2 + 4 * a) * F, depth, 12)
+        elif paired:
             t_upd[a] = bench("%s[%d]" % (upd, a), 13, 1 + 2 * a, a, (2 + 4 * a) * F, 2, 12)
         else:
             t_upd[a] = bench("%s[%d]" % (upd, a), 4, 1 + 2 * a, a, (2 + 4 * a) * F, 1, 12)

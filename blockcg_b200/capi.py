@@ -30,7 +30,7 @@ EXPORTS = [
     "bcg_add", "bcg_add_scalar", "bcg_rescale_add", "bcg_trsm", "bcg_thinqr", "bcg_true_residual",
     "bcg_solve_bcg_dev", "bcg_solve_bcgrq_dev", "bcg_solve_sbcgrq_dev", "bcg_solve_bcg", "bcg_solve_bcgrq",
     "bcg_solve_sbcgrq", "bcg_bench_kernel", "bcg_solve_cg_dev", "bcg_solve_scg_dev", "bcg_solve_cg", "bcg_solve_scg",
-    "bcg_last_solve_stats", "bcg_small_inverse", "bcg_small_lu_solve", "bcg_set_loop_profile", "bcg_get_loop_profile", "bcg_shift_schedule",
+    "bcg_last_solve_stats", "bcg_small_inverse", "bcg_small_lu_solve", "bcg_set_loop_profile", "bcg_get_loop_profile", "bcg_shift_schedule", "bcg_stag_schedule",
 ]
 
 
@@ -43,7 +43,7 @@ class SolveInfo(C.Structure):
 
 
 class SolveStats(C.Structure):
-    _fields_ = [("iterations", C.c_int), ("n_shifts", C.c_int), ("paired", C.c_int),
+    _fields_ = [("iterations", C.c_int), ("n_shifts", C.c_int), ("paired", C.c_int), ("depth", C.c_int),
                 ("active_hist", C.c_uint32 * (MAX_SHIFTS + 1)), ("shift_update_field_passes", C.c_uint64),
                 ("resid_shift", C.c_double * MAX_SHIFTS)]
 
@@ -122,6 +122,7 @@ def load():
     lib.bcg_set_loop_profile.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.bcg_get_loop_profile.argtypes = [C.c_void_p, C.POINTER(LoopProfile)]
     lib.bcg_shift_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip]
+    lib.bcg_stag_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip]
     lib.bcg_small_inverse.argtypes = [C.c_void_p, _dp, _dp, C.c_int, _ip]
     lib.bcg_small_lu_solve.argtypes = [C.c_void_p, _dp, _dp, _dp]
     lib.bcg_bench_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _ip, C.c_int, _dp,
@@ -150,6 +151,21 @@ def shift_schedule(schedule, iteration, stop, n_active, n_active_prev):
     passes = C.c_int(0)
     n = lib.bcg_shift_schedule(schedule, iteration, 1 if stop else 0, n_active, n_active_prev, kinds, systems, C.byref(passes))
     return [(kinds[i], systems[i]) for i in range(n)], passes.value
+
+
+def stag_schedule(depth, iteration, stop, n_active, n_active_ring, ring=None, part=0):
+    """Items of one launch of the depth-`depth` staggered update (schedule 3): [(system, first_back, n_updates)],
+    field passes (host-side, no device).  n_active_ring[j % ring] = active systems of the earlier iteration j;
+    part = 0 whole launch, 1 / 2 the two launches of the overlapped variant (ring = depth + 1)."""
+    lib = load()
+    n_max = MAX_SHIFTS + 2
+    systems, first, count = (C.c_int * n_max)(), (C.c_int * n_max)(), (C.c_int * n_max)()
+    ringv = (C.c_int * 4)(*([int(v) for v in n_active_ring] + [0] * 4)[:4])
+    passes = C.c_int(0)
+    n = lib.bcg_stag_schedule(depth, ring or depth, part, iteration, 1 if stop else 0, n_active, ringv, systems, first,
+                              count, C.byref(passes))
+    assert n >= 0, "bad argument to bcg_stag_schedule"
+    return [(systems[i], first[i], count[i]) for i in range(n)], passes.value
 
 
 class Context:
@@ -359,7 +375,7 @@ class Context:
         estimates of the last solve on this context."""
         st = SolveStats()
         self._ck(self.lib.bcg_last_solve_stats(self._h, C.byref(st)))
-        return {"iterations": st.iterations, "n_shifts": st.n_shifts, "paired": bool(st.paired),
+        return {"iterations": st.iterations, "n_shifts": st.n_shifts, "paired": bool(st.paired), "schedule": st.paired, "depth": st.depth,
                 "active_hist": list(st.active_hist), "shift_update_field_passes": int(st.shift_update_field_passes),
                 "resid_shift": list(st.resid_shift)[:max(st.n_shifts, 1)]}
 

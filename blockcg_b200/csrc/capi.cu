@@ -117,8 +117,14 @@ struct bcg_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // 4-D slabs: halo exchange overlapped with the interior sweeps
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // overlapped multishift update (schedule 3 + BCG_OVERLAP): the shifted systems' launch runs on a second stream of
+  // lower priority beside the next iterations' kernels (shift_stag.cuh)
+  cudaStream_t stream_bulk = nullptr;
+  cudaEvent_t ev_crit = nullptr, ev_bulk[2] = {nullptr, nullptr};
+  int loop_unit = 2;  // graph batches and profile windows are multiples of this many iterations
   const OpsTable* ops = nullptr;
   cd* U_alloc = nullptr;
+  cd* Ut_alloc = nullptr;  // 4-D: the links once more, direction-major [mu][site][3][3] (dirac4_tile.cuh)
   std::vector<cd*> fields;  // allocation base (halo included); site 0 at +2*3N
   cd* gpart = nullptr;
   size_t gpart_elems = 0;
@@ -131,6 +137,7 @@ struct bcg_ctx {
   cd* mat_host = nullptr;     // pinned staging for N*N matrices (4 slots)
   int work_T = -1, work_Q = -1;
   int work_Qp = -1;   // Q of the previous iteration (paired multishift update)
+  int work_Qh[2] = {-1, -1};  // two more Q fields for the deferral of depth 3 / 4 (ring of Q fields)
   Ctrl* bench_ctrl = nullptr;  // micro-benchmark of the paired update: control blocks of an odd and an even iteration
   std::vector<int> work_P;
   std::vector<int> host_X;  // handles used by the host-buffer entry points
@@ -192,6 +199,8 @@ inline size_t site_elems(const bcg_ctx* c) { return static_cast<size_t>(3) * c->
 inline size_t field_elems(const bcg_ctx* c) { return static_cast<size_t>(c->cap + c->halo) * site_elems(c); }
 inline cd* fptr(const bcg_ctx* c, int h) { return c->fields[h] + c->halo * site_elems(c); }
 inline cd* uptr(const bcg_ctx* c) { return c->U_alloc + c->halo * c->links_site; }
+inline long long ut_stride(const bcg_ctx* c) { return c->cap + c->halo; }            // sites per direction of Ut
+inline cd* utptr(const bcg_ctx* c) { return c->Ut_alloc + c->halo * 9; }             // site 0 of direction 0
 inline bool valid(const bcg_ctx* c, int h) {
   return h >= 0 && h < static_cast<int>(c->fields.size()) && c->fields[h] != nullptr;
 }
@@ -336,6 +345,30 @@ int gram_to_gred(bcg_ctx* c, const cd* a, const cd* b, int* launches) {
   return BCG_OK;
 }
 
+// BCG_DIRAC4_TILE=0 selects the first-generation 4-D sweep (dirac4d.cuh) for comparison
+bool dirac4_tile_default() {
+  const char* e = std::getenv("BCG_DIRAC4_TILE");
+  return e ? std::atoi(e) != 0 : true;
+}
+
+// one sweep of the 4-D operator over the sites [x_begin, x_end) (whole x0-rows): the tiled kernel where the lattice
+// allows it, else the gather kernel.  gpart != nullptr: fused partial Gram p0^dag out (returns their number, 0 if
+// the sweep that ran cannot fuse it).
+int sweep4(bcg_ctx* c, const cd* in, const cd* p0, cd* out, long long x_begin, long long x_end, double m2, double sigma,
+           int second, cd* gpart, const Ctrl* ctrl, int* launches) {
+  if (c->ops->dirac4_tile != nullptr && c->Ut_alloc != nullptr && dirac4_tile_default()) {
+    const long long L0 = c->lat.L0;
+    int np = c->ops->dirac4_tile(c->stream, in, p0, out, utptr(c), &c->lat, ut_stride(c), x_begin / L0, x_end / L0, m2, sigma,
+                                 second, gpart, ctrl, c->sms, launches);
+    if (np == -static_cast<int>(cudaErrorNotSupported) && gpart != nullptr)  // this N cannot fuse the Gram: plain sweep
+      np = c->ops->dirac4_tile(c->stream, in, p0, out, utptr(c), &c->lat, ut_stride(c), x_begin / L0, x_end / L0, m2, sigma,
+                               second, nullptr, ctrl, c->sms, launches);
+    if (np != -static_cast<int>(cudaErrorNotSupported)) return np;
+  }
+  const int e = c->ops->dirac4_sweep(c->stream, in, p0, out, uptr(c), &c->lat, x_begin, x_end, m2, sigma, second, ctrl, launches);
+  return e < 0 ? e : 0;  // < 0: -cudaError (as the launchers return it; the caller wraps it with KL)
+}
+
 // out = (m^2 + sigma) in - D(D in), optionally with the partial Gram in^dag out in c->gpart.
 // `in` must have a valid halo.  Returns the number of partial Gram blocks (0 if none) or < 0.
 // 1-D chain: one fused kernel.  4-D: two sweeps through the intermediate field (whose halo is
@@ -360,8 +393,8 @@ int apply_op(bcg_ctx* c, cd* in, cd* out, double sigma, bool want_gram, const Ct
     // Slab decomposition: the halo exchange of the intermediate field is overlapped with the
     // interior.  Boundary slices of sweep 1 first; their exchange (NVLink, second stream) runs
     // while both sweeps of the interior slices are computed; boundary slices of sweep 2 last.
-    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, 0, H, m2, sigma, 0, ctrl, launches));
-    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, V - H, V, m2, sigma, 0, ctrl, launches));
+    KL(sweep4(c, in, nullptr, tmp, 0, H, m2, sigma, 0, nullptr, ctrl, launches));
+    KL(sweep4(c, in, nullptr, tmp, V - H, V, m2, sigma, 0, nullptr, ctrl, launches));
     CU(cudaEventRecord(c->ev_fork, c->stream));
     CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
     cudaStream_t main_stream = c->stream;
@@ -370,16 +403,22 @@ int apply_op(bcg_ctx* c, cd* in, cd* out, double sigma, bool want_gram, const Ct
     c->stream = main_stream;
     if (r) return r;
     CU(cudaEventRecord(c->ev_join, c->stream2));
-    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, H, V - H, m2, sigma, 0, ctrl, launches));
-    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, H, V - H, m2, sigma, 1, ctrl, launches));
+    KL(sweep4(c, in, nullptr, tmp, H, V - H, m2, sigma, 0, nullptr, ctrl, launches));
+    KL(sweep4(c, tmp, in, out, H, V - H, m2, sigma, 1, nullptr, ctrl, launches));
     CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, 0, H, m2, sigma, 1, ctrl, launches));
-    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, V - H, V, m2, sigma, 1, ctrl, launches));
+    KL(sweep4(c, tmp, in, out, 0, H, m2, sigma, 1, nullptr, ctrl, launches));
+    KL(sweep4(c, tmp, in, out, V - H, V, m2, sigma, 1, nullptr, ctrl, launches));
   } else {
-    KL(c->ops->dirac4_sweep(c->stream, in, nullptr, tmp, uptr(c), &c->lat, 0, V, m2, sigma, 0, ctrl, launches));
+    KL(sweep4(c, in, nullptr, tmp, 0, V, m2, sigma, 0, nullptr, ctrl, launches));
     int r = halo_refresh(c, tmp, 3 * c->N, ctrl, launches);
     if (r) return r;
-    KL(c->ops->dirac4_sweep(c->stream, tmp, in, out, uptr(c), &c->lat, 0, V, m2, sigma, 1, ctrl, launches));
+    // one rank, one launch over the whole volume: the sweep accumulates the Gram of its tiles on the way
+    const int np = sweep4(c, tmp, in, out, 0, V, m2, sigma, 1, want_gram ? c->gpart : nullptr, ctrl, launches);
+    KL(np);
+    if (want_gram && np > 0) {
+      *np_out = np;
+      return BCG_OK;
+    }
   }
   *np_out = 0;
   if (want_gram) {
@@ -395,6 +434,27 @@ int upload_mat(bcg_ctx* c, int slot, const double* host, int staging) {
   std::memcpy(c->mat_host + staging * nn, host, nn * sizeof(cd));
   CU(cudaMemcpyAsync(mat(c, slot), c->mat_host + staging * nn, nn * sizeof(cd), cudaMemcpyHostToDevice, c->stream));
   return BCG_OK;
+}
+
+int pair_default(const bcg_ctx* c);
+// Deferral depth of schedule 3 (BCG_PAIR=3): BCG_DEPTH = 2, 3 or 4
+int depth_default() {
+  const char* e = std::getenv("BCG_DEPTH");
+  int d = e ? std::atoi(e) : 4;
+  return d < 2 ? 2 : (d > kMaxDepth ? kMaxDepth : d);
+}
+
+// The shifted systems' launch beside the next iterations' kernels (schedule 3 only): BCG_OVERLAP = 0 / 1;
+// default: on for a slab decomposition over four or more ranks (where the coefficient kernels' latency chains
+// dominate the iteration), off otherwise.  BCG_BULK_CTAS caps that launch's grid (0: as many as fit).
+int overlap_default(const bcg_ctx* c) {
+  const char* e = std::getenv("BCG_OVERLAP");
+  if (e) return std::atoi(e) != 0;
+  return 0;
+}
+int bulk_ctas_default() {
+  const char* e = std::getenv("BCG_BULK_CTAS");
+  return e ? std::atoi(e) : 0;
 }
 
 int ensure_work(bcg_ctx* c, int n_shifts) {
@@ -414,6 +474,12 @@ int ensure_work(bcg_ctx* c, int n_shifts) {
     int r = field_alloc(c, &c->work_Qp);
     if (r) return r;
   }
+  if (n_shifts > 1 && c->ops->shift_update_stag && c->work_Qp >= 0 && pair_default(c) == 3)
+    for (int t = 0; t < depth_default() + 1 - 2 && t < 2; ++t)  // ring of depth (+ 1: overlapped launch) Q fields
+      if (c->work_Qh[t] < 0) {
+        int r = field_alloc(c, &c->work_Qh[t]);
+        if (r) return r;
+      }
   while (static_cast<int>(c->work_P.size()) < n_shifts) {
     int h;
     int r = field_alloc(c, &h);
@@ -485,7 +551,14 @@ static int ctx_create(bcg_ctx** out, int64_t v_local, const int64_t* dims, int n
   c->ops->prepare(c->sms);
   c->cap = c->ops->field_capacity(c->V, c->sms);
   if (c->cap < c->V + c->halo) c->cap = c->V + c->halo;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int prio_low = 0, prio_high = 0;  // the loop's stream outranks the stream of the overlapped update
+    CU(cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high));
+    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_high));
+    CU(cudaStreamCreateWithPriority(&c->stream_bulk, cudaStreamNonBlocking, prio_low));
+    CU(cudaEventCreateWithFlags(&c->ev_crit, cudaEventDisableTiming));
+    for (auto& e : c->ev_bulk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -504,6 +577,10 @@ static int ctx_create(bcg_ctx** out, int64_t v_local, const int64_t* dims, int n
   CU(cudaMallocHost(&c->mat_host, 4 * c->L.nn() * sizeof(cd)));
   CU(cudaMalloc(&c->U_alloc, static_cast<size_t>(c->cap + c->halo) * c->links_site * sizeof(cd)));
   CU(cudaMemset(c->U_alloc, 0, static_cast<size_t>(c->cap + c->halo) * c->links_site * sizeof(cd)));
+  if (c->ndim == 4 && c->ops->dirac4_tile != nullptr) {
+    CU(cudaMalloc(&c->Ut_alloc, static_cast<size_t>(c->cap + c->halo) * 36 * sizeof(cd)));
+    CU(cudaMemset(c->Ut_alloc, 0, static_cast<size_t>(c->cap + c->halo) * 36 * sizeof(cd)));
+  }
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   for (auto& e : c->ev_batch) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if ((1 + kRedSlices) * c->L.nn() * sizeof(cd) > 48 * 1024)  // N = 32: the stand-alone Gram reduction needs the opt-in too
@@ -547,6 +624,7 @@ int bcg_ctx_destroy(bcg_ctx* c) {
   for (cd* p : c->fields)
     if (p) cudaFree(p);
   cudaFree(c->U_alloc);
+  cudaFree(c->Ut_alloc);
   cudaFree(c->gpart);
   cudaFree(c->gred);
   cudaFree(c->mats);
@@ -560,6 +638,10 @@ int bcg_ctx_destroy(bcg_ctx* c) {
   for (auto& e : c->ev_batch)
     if (e) cudaEventDestroy(e);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_crit) cudaEventDestroy(c->ev_crit);
+  for (auto& e : c->ev_bulk)
+    if (e) cudaEventDestroy(e);
+  if (c->stream_bulk) cudaStreamDestroy(c->stream_bulk);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -629,6 +711,16 @@ int bcg_comm_ipc_open(bcg_ctx* c, const void* handles) {
   return BCG_OK;
 }
 
+// 4-D: the direction-major copy of the links (halo slices included) the tiled sweep streams row by row
+static int links_transposed(bcg_ctx* c) {
+  if (c->ndim != 4 || c->Ut_alloc == nullptr) return BCG_OK;
+  const long long n_sites = c->V + 2 * c->halo;
+  const unsigned blocks = static_cast<unsigned>(std::min<long long>((n_sites * 36 + 255) / 256, 148LL * 16));
+  links4_transpose_kernel<<<blocks, 256, 0, c->stream>>>(utptr(c), uptr(c), -c->halo, n_sites, ut_stride(c));
+  CU(cudaGetLastError());
+  return BCG_OK;
+}
+
 static int set_links(bcg_ctx* c, const double* links_host, double mass, int ndim) {
   if (!c || !links_host) return fail(c, BCG_ERR_INVALID, "null argument");
   if (c->ndim != ndim)
@@ -637,6 +729,8 @@ static int set_links(bcg_ctx* c, const double* links_host, double mass, int ndim
   CU(cudaMemcpyAsync(uptr(c), links_host, static_cast<size_t>(c->V) * c->links_site * sizeof(cd),
                      cudaMemcpyHostToDevice, c->stream));
   int r = halo_refresh(c, uptr(c), c->links_site, nullptr, nullptr);
+  if (r) return r;
+  r = links_transposed(c);
   if (r) return r;
   CU(cudaStreamSynchronize(c->stream));
   c->mass = mass;
@@ -676,6 +770,8 @@ int bcg_set_links_random(bcg_ctx* c, uint64_t seed, double mass) {
   int r = fill_uniform(c, uptr(c), c->links_site, seed, /*stream*/ 0);
   if (r) return r;
   r = halo_refresh(c, uptr(c), c->links_site, nullptr, nullptr);
+  if (r) return r;
+  r = links_transposed(c);
   if (r) return r;
   CU(cudaStreamSynchronize(c->stream));
   c->mass = mass;
@@ -857,9 +953,14 @@ namespace {
 
 // Schedule of the multishift update (build_shift_items in common.cuh): BCG_PAIR = 0 plain, 1 alternating,
 // 2 staggered (default where the kernels support it).
-int pair_default() {  // read per solve, so that a test can compare the schedules in one process
+// Default: 3 (every fourth iteration) from kDeepDeferralMinSites sites per rank on -- measured 3 % faster than
+// schedule 2 at 24^4 and 8 % slower at 41 k sites, where the launch's fixed costs count
+// (profiles/r02_ab_shift_depth_and_overlap.jsonl).
+constexpr long long kDeepDeferralMinSites = 250000;
+int pair_default(const bcg_ctx* c) {  // read per solve, so that a test can compare the schedules in one process
   const char* e = std::getenv("BCG_PAIR");
-  return e ? std::atoi(e) : 2;
+  if (e) return std::atoi(e);
+  return (c->V >= kDeepDeferralMinSites && c->ndim == 1) ? 3 : 2;
 }
 
 // The (S)BCGrQ update on the FP64 tensor instruction (shift_dmma.cuh).  BCG_DMMA=0 selects the DFMA kernels.
@@ -888,7 +989,11 @@ struct LoopPlan {
   int kind;  // 0 BCG, 1 (S)BCGrQ, 2 CG / SCG (scalar coefficients, N_rhs = 1)
   int n_shifts;
   int pair;   // schedule of the multishift update: 0 plain, 1 alternating, 2 staggered (build_shift_items)
-  cd* Qbuf[2];  // staggered schedule: the two Q fields ([0] holds Q of even iteration numbers, incl. the initial one)
+  cd* Qbuf[kMaxDepth];  // staggered schedules: the ring of Q fields (Q of iteration i in [i % depth], the initial one in [0])
+  int depth;    // deferral depth (2 for the schedules 1 and 2)
+  int ring;     // Q fields / operand sets in use (= depth, or depth + 1 with the overlapped launch)
+  bool overlap; // schedule 3: the shifted systems' launch goes to c->stream_bulk and runs beside the next iterations
+  int bulk_ctas;
   bool dmma;  // (S)BCGrQ update by shift_dmma_kernel (plain or paired schedule)
   int nthr;   // threads of the coefficient kernels
   bool fold_halo;  // the update kernel refreshes the halo of P0 itself (no halo kernel in the loop)
@@ -903,7 +1008,9 @@ struct LoopPlan {
 // marks (optional): 7 events, recorded before the stencil and after each of the six stages
 // (stencil+Gram, A-step, Q update+Gram, B-step, multishift update, halo)
 // pos: iterations completed before this one (its parity selects the Q field of the staggered schedule)
-int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t* marks = nullptr, int pos = 0) {
+// rel: position in the graph being captured / in the profile window (the overlapped launch of iteration rel - 2
+// was forked inside the same capture and is joined before this iteration's Q update)
+int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t* marks = nullptr, int pos = 0, int rel = 0) {
 #define BCG_MARK(i) do { if (marks) CU(cudaEventRecord(marks[i], c->stream)); } while (0)
   BCG_MARK(0);
   const cd* gsrc;
@@ -971,8 +1078,11 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   BCG_MARK(2);
   // staggered schedule: Q ping-pongs between two fields -- Q_pos (the previous iteration's, kept intact for the
   // deferred updates) is read, the new Q is written into the other one and normalised there by the update kernel
-  cd* Qin = (p.pair == 2) ? p.Qbuf[pos & 1] : p.Q;
-  cd* Qout = (p.pair == 2) ? p.Qbuf[(pos + 1) & 1] : p.Q;
+  cd* Qin = (p.pair >= 2) ? p.Qbuf[pos % p.ring] : p.Q;
+  cd* Qout = (p.pair >= 2) ? p.Qbuf[(pos + 1) % p.ring] : p.Q;
+  // overlapped launch of two iterations ago: it reads the Q field this update overwrites, the operand sets and the
+  // snapshot slot this iteration's B-step overwrites
+  if (p.overlap && rel >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_bulk[(pos + 1) & 1], 0));
   np = c->ops->axpy_gram(c->stream, Qin, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches,
                          fused ? &gp1 : nullptr, Qout);
   KL(np);
@@ -988,7 +1098,25 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   ++*launches;
   CU(cudaGetLastError());
   BCG_MARK(4);
-  if (p.dmma)
+  if (p.pair == 3) {
+    ShiftStagCoefs co;
+    std::memset(&co, 0, sizeof co);
+    for (int t = 0; t < kMaxDepth; ++t) {
+      co.A[t] = c->mats + c->L.Aset(0, t < p.ring ? t : 0);
+      co.B[t] = c->mats + c->L.Bset(0, t < p.ring ? t : 0);
+    }
+    KL(c->ops->shift_update_stag(c->stream, p.Qbuf, p.depth, p.ring, p.overlap ? 1 : 0, 0, 0, &p.fp, mat(c, M_RHO_CUR), &co, c->V,
+                                 c->ctrl, c->sms, launches, (p.fold_halo && c->nranks == 1) ? p.P0 : nullptr,
+                                 fold_mg ? &hf : nullptr));
+    if (p.overlap) {
+      const int slot = (pos + 1) & 1;  // this iteration's number is pos + 1 (mod 2: batches are even)
+      CU(cudaEventRecord(c->ev_crit, c->stream));
+      CU(cudaStreamWaitEvent(c->stream_bulk, c->ev_crit, 0));
+      KL(c->ops->shift_update_stag(c->stream_bulk, p.Qbuf, p.depth, p.ring, 2, slot, p.bulk_ctas, &p.fp, mat(c, M_RHO_CUR), &co,
+                                   c->V, c->ctrl, c->sms, launches, nullptr, nullptr));
+      CU(cudaEventRecord(c->ev_bulk[slot], c->stream_bulk));
+    }
+  } else if (p.dmma)
     KL(c->ops->shift_update_dmma(c->stream, Qout, p.pair == 2 ? Qin : (p.pair == 1 ? fptr(c, c->work_Qp) : nullptr), &p.fp,
                                  mat(c, M_RHO_CUR), c->mats + c->L.A(0, 1), c->mats + c->L.B(0, 1), c->mats + c->L.A(0, 0),
                                  c->mats + c->L.B(0, 0), c->V, c->ctrl, c->sms, launches, p.pair,
@@ -1010,9 +1138,23 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
 #undef BCG_MARK
 }
 
+// the loop's stream waits for the overlapped launches forked by the last `n` iterations enqueued
+int join_bulk(bcg_ctx* c, const LoopPlan& p, int n) {
+  if (!p.overlap) return BCG_OK;
+  if (n >= 2) {  // n is a multiple of loop_unit (even): both events were recorded by these iterations
+    CU(cudaStreamWaitEvent(c->stream, c->ev_bulk[0], 0));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_bulk[1], 0));
+  }
+  return BCG_OK;
+}
+
 int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launches_total) {
   int batch = pick_batch(c, p.n_shifts);
-  batch += batch & 1;  // even: an iteration's position in the batch then has the parity of its number (staggered schedule)
+  {  // a multiple of 2 and of the ring size: an iteration's position in the batch then fixes its Q field
+    const int unit = (p.pair == 3 && p.ring == 3) ? 6 : (p.pair == 3 && p.ring == 4) ? 4 : 2;
+    batch = (batch + unit - 1) / unit * unit;
+    c->loop_unit = unit;
+  }
   // (re)build the graph of `batch` iterations if anything it bakes in changed
   std::vector<const void*> key = {p.P0, p.T, p.Q};
   for (int s = 0; s < p.n_shifts; ++s) {
@@ -1028,7 +1170,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     key.push_back(bits);
   }
   key.push_back(p.pair ? &c->work_Qp : nullptr);
-  key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(p.pair)));
+  key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(((p.bulk_ctas * 2 + (p.overlap ? 1 : 0)) * 8 + p.ring) * 64 + p.pair * 16 + p.depth)));
   key.push_back(p.dmma ? &c->work_Q : nullptr);
   key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(p.nthr * 2 + (p.fold_halo ? 1 : 0))));
   GraphCache& g = c->graph;
@@ -1041,7 +1183,8 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int r = BCG_OK;
-    for (int i = 0; i < batch && r == BCG_OK; ++i) r = enqueue_iteration(c, p, &launches, nullptr, i);
+    for (int i = 0; i < batch && r == BCG_OK; ++i) r = enqueue_iteration(c, p, &launches, nullptr, i, i);
+    if (r == BCG_OK) r = join_bulk(c, p, batch);
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     if (r != BCG_OK) {
       if (graph) cudaGraphDestroy(graph);
@@ -1065,7 +1208,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
     if (c->prof_want > 0 && submitted * batch >= c->prof_after) {
       // in-loop profile: the next iterations one kernel at a time with an event after each stage (same
       // kernels, same stream, same control flow on the device; only the submission differs)
-      const int P = c->prof_want;
+      const int P = (c->prof_want + c->loop_unit - 1) / c->loop_unit * c->loop_unit;  // the graph resumes at a position 0
       c->prof_want = 0;  // one window, one solve
       while (static_cast<int>(c->prof_ev.size()) < 7 * P) {
         cudaEvent_t e;
@@ -1077,7 +1220,11 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
       const int first = c->ctrl_host[0].iter;
       int l = 0;
       for (int i = 0; i < P; ++i) {
-        int r = enqueue_iteration(c, p, &l, c->prof_ev.data() + 7 * i, first + i);
+        int r = enqueue_iteration(c, p, &l, c->prof_ev.data() + 7 * i, first + i, i);
+        if (r) return r;
+      }
+      {
+        int r = join_bulk(c, p, P);
         if (r) return r;
       }
       *launches_total += l;
@@ -1183,11 +1330,23 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   r = init_ctrl(c, n_shifts, sigma, eps, eps_shifts, max_it);
   if (r) return r;
   const bool dmma = dmma_default() && c->ops->shift_update_dmma != nullptr;
-  int pair = (n_shifts > 1 && c->work_Qp >= 0) ? pair_default() : 0;
+  int pair = (n_shifts > 1 && c->work_Qp >= 0) ? pair_default(c) : 0;
+  int depth = 2;
+  if (pair == 3) {
+    depth = depth_default();
+    const bool have_ring = (depth <= 2 || c->work_Qh[0] >= 0) && (depth <= 3 || c->work_Qh[1] >= 0);
+    if (!(dmma && c->ops->out_of_place_axpy && c->ops->shift_update_stag && have_ring)) pair = 2;
+  }
   if (pair == 2 && !(dmma && c->ops->out_of_place_axpy)) pair = 1;  // staggering needs the tensor-instruction kernel and Q ping-pong
   if (pair == 1 && !(dmma || c->ops->shift_update_pair != nullptr)) pair = 0;
-  if (pair < 0 || pair > 2) pair = 0;
+  if (pair < 0 || pair > 3) pair = 0;
+  if (pair != 3) depth = 2;
+  bool overlap = pair == 3 && overlap_default(c) != 0 && depth + 1 <= kMaxDepth && c->work_Qh[depth - 2] >= 0;
+  const int ring = depth + (overlap ? 1 : 0);
   c->L.pair = pair;
+  c->L.depth = depth;
+  c->L.ring = ring;
+  c->L.overlap = overlap ? 1 : 0;
   int64_t launches = 0;
   int l = 0;
   CU(cudaEventRecord(c->ev[0], c->stream));
@@ -1218,8 +1377,14 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   // and the next stencil waits for them and unpacks them itself (needs the parity-chain stencil: N = 4, 8, 12, 16).
   p.fold_halo = dmma && c->ndim == 1 && c->V >= 4 && c->V % 2 == 0 && fold_halo_default() &&
                 (c->nranks == 1 || (c->p2p_ready && c->ops->fused_exchange));
+  p.depth = depth;
+  p.ring = ring;
+  p.overlap = overlap;
+  p.bulk_ctas = overlap ? bulk_ctas_default() : 0;
   p.Qbuf[0] = Q;
-  p.Qbuf[1] = (pair == 2) ? fptr(c, c->work_Qp) : Q;
+  p.Qbuf[1] = (pair >= 2) ? fptr(c, c->work_Qp) : Q;
+  p.Qbuf[2] = (pair == 3 && ring >= 3) ? fptr(c, c->work_Qh[0]) : Q;
+  p.Qbuf[3] = (pair == 3 && ring >= 4) ? fptr(c, c->work_Qh[1]) : Q;
   p.n_shifts = n_shifts;
   p.T = fptr(c, c->work_T);
   p.Q = Q;
@@ -1478,6 +1643,7 @@ int bcg_last_solve_stats(bcg_ctx* c, bcg_solve_stats* out) {
   out->iterations = h.iter;
   out->n_shifts = h.n_shifts;
   out->paired = c->L.pair;
+  out->depth = c->L.pair ? c->L.depth : 1;
   for (int a = 0; a <= BCG_MAX_SHIFTS; ++a) out->active_hist[a] = h.hist[a];
   out->shift_update_field_passes = h.shift_passes;
   for (int s2 = 0; s2 < BCG_MAX_SHIFTS; ++s2) out->resid_shift[s2] = h.resid_shift[s2];
@@ -1496,6 +1662,24 @@ int bcg_shift_schedule(int schedule, int iteration, int stop, int n_active, int 
   for (int i = 0; i < n; ++i) {
     if (kinds) kinds[i] = items[i].kind;
     if (systems) systems[i] = items[i].s;
+  }
+  if (field_passes) *field_passes = passes;
+  return n;
+}
+
+// Host-side view of schedule 3 (build_stag_items): n_active_ring[j % ring] = systems active in iteration j for the
+// depth-1 iterations before `iteration`; part = 0 whole launch / 1 Q and system 0 / 2 the shifted systems only.  systems[i] = -1 for the Q item; first_back[i] / n_updates[i]: the item's
+// first pending update is that of iteration `iteration - first_back[i]`, n_updates[i] consecutive ones follow.
+int bcg_stag_schedule(int depth, int ring, int part, int iteration, int stop, int n_active, const int* n_active_ring,
+                      int* systems, int* first_back, int* n_updates, int* field_passes) {
+  if (depth < 2 || ring < depth || ring > kMaxDepth || part < 0 || part > 2 || !n_active_ring) return -1;
+  StagItem items[kMaxShiftItems];
+  int passes = 0;
+  const int n = build_stag_items(depth, ring, part, iteration, stop, n_active, n_active_ring, items, &passes);
+  for (int i = 0; i < n; ++i) {
+    if (systems) systems[i] = items[i].s;
+    if (first_back) first_back[i] = items[i].d_first;
+    if (n_updates) n_updates[i] = items[i].m;
   }
   if (field_passes) *field_passes = passes;
   return n;
@@ -1567,7 +1751,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   const double m2 = c->mass * c->mass;
   ShiftPtrs fp;
   std::memset(&fp, 0, sizeof fp);
-  if (which == 4 || which == 7 || which == 8 || which == 13) {
+  if (which == 4 || which == 7 || which == 8 || which == 13 || which == 14) {
     if (nh < 1 + 2 * n_shifts || n_shifts < 1 || n_shifts > c->S) return fail(c, BCG_ERR_INVALID, "need 1+2S handles");
     for (int s = 0; s < n_shifts; ++s) {
       fp.X[s] = fptr(c, h[1 + 2 * s]);
@@ -1578,9 +1762,11 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
   }
   MatLayout Lp = c->L;
   Lp.pair = 1;
+  Lp.depth = Lp.ring = 2;
+  Lp.overlap = 0;
   const bool use_dmma = dmma_default() && c->ops->shift_update_dmma != nullptr && (which == 13 || which == 4);
   // schedule the paired micro-benchmark runs (as solve_rq picks it)
-  int bench_sched = pair_default();
+  int bench_sched = pair_default(c);
   if (bench_sched == 2 && !(use_dmma && c->ops->out_of_place_axpy)) bench_sched = 1;
   if (bench_sched < 1 || bench_sched > 2) bench_sched = 1;
   if (which == 13 || (which == 4 && use_dmma)) {  // paired multishift update: one repetition = an odd and an even iteration's launch
@@ -1589,7 +1775,7 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
       int r_ = field_alloc(c, &c->work_Qp);
       if (r_) return r_;
     }
-    if (!c->bench_ctrl) CU(cudaMalloc(&c->bench_ctrl, 2 * sizeof(Ctrl)));
+    if (!c->bench_ctrl) CU(cudaMalloc(&c->bench_ctrl, kMaxDepth * sizeof(Ctrl)));
     Ctrl hc[2];
     std::memset(hc, 0, sizeof hc);
     for (int i = 0; i < 2; ++i) {
@@ -1600,8 +1786,45 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
     }
     CU(cudaMemcpy(c->bench_ctrl, hc, sizeof hc, cudaMemcpyHostToDevice));
   }
+  // schedule 3 (shift_stag.cuh): one repetition = `depth` consecutive steady-state launches (every group served once)
+  const int sdepth = depth_default();
+  cd* qring[kMaxDepth] = {nullptr, nullptr, nullptr, nullptr};
+  ShiftStagCoefs sco;
+  std::memset(&sco, 0, sizeof sco);
+  if (which == 14) {
+    if (!c->ops->shift_update_stag) return fail(c, BCG_ERR_INVALID, "no staggered multishift kernel at N=%d", c->N);
+    int* extra[3] = {&c->work_Qp, &c->work_Qh[0], &c->work_Qh[1]};
+    for (int t = 0; t < sdepth - 1; ++t)
+      if (*extra[t] < 0) {
+        int r_ = field_alloc(c, extra[t]);
+        if (r_) return r_;
+      }
+    qring[0] = fptr(c, h[0]);
+    for (int t = 1; t < kMaxDepth; ++t) qring[t] = t < sdepth ? fptr(c, *extra[t - 1]) : qring[0];
+    Lp.pair = 3;
+    Lp.depth = Lp.ring = sdepth;
+    for (int t = 0; t < kMaxDepth; ++t) {
+      sco.A[t] = c->mats + Lp.Aset(0, t < sdepth ? t : 0);
+      sco.B[t] = c->mats + Lp.Bset(0, t < sdepth ? t : 0);
+    }
+    if (!c->bench_ctrl) CU(cudaMalloc(&c->bench_ctrl, kMaxDepth * sizeof(Ctrl)));
+    std::vector<Ctrl> hc(kMaxDepth);
+    std::memset(hc.data(), 0, kMaxDepth * sizeof(Ctrl));
+    for (int i = 0; i < kMaxDepth; ++i) {
+      hc[i].iter = 2 * sdepth + i;
+      hc[i].n_unconv = n_shifts;
+      hc[i].n_shifts = n_shifts;
+      for (int t = 0; t < 4; ++t) hc[i].n_act[t] = n_shifts;
+    }
+    CU(cudaMemcpy(c->bench_ctrl, hc.data(), kMaxDepth * sizeof(Ctrl), cudaMemcpyHostToDevice));
+  }
   auto body = [&](int* l) -> int {
     switch (which) {
+      case 14:
+        for (int i = 0; i < sdepth; ++i)
+          KL(c->ops->shift_update_stag(c->stream, qring, sdepth, sdepth, 0, 0, 0, &fp, mat(c, M_SCRATCH), &sco, c->V,
+                                       c->bench_ctrl + i, c->sms, l, nullptr, nullptr));
+        break;
       case 13:
         for (int i = 0; i < 2; ++i) {
           if (use_dmma)
@@ -1684,12 +1907,16 @@ int bcg_bench_kernel(bcg_ctx* c, int which, int reps, int n_shifts, const int* h
     std::vector<cd> I(nn, make_double2(0, 0)), Z(nn, make_double2(0, 0));
     for (int i = 0; i < c->N; ++i) I[i + c->N * i] = make_double2(1.0, 0.0);
     for (size_t e = 0; e < nn; ++e) Z[e] = make_double2(1e-3 * ((e * 7) % 5), -1e-3 * ((e * 3) % 7));
-    CU(cudaMemcpy(mat(c, M_SCRATCH), (which == 4 || which == 7 || which == 8 || which == 13) ? I.data() : Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(mat(c, M_SCRATCH), (which == 4 || which == 7 || which == 8 || which == 13 || which == 14) ? I.data() : Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
     for (int s = 0; s < c->S; ++s) {
       CU(cudaMemcpy(c->mats + c->L.A(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(c->mats + c->L.B(s), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(c->mats + Lp.A(s, 1), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(c->mats + Lp.B(s, 1), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+      for (int t = 1; t < kMaxDepth && which == 14; ++t) {
+        CU(cudaMemcpy(c->mats + Lp.Aset(s, t), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->mats + Lp.Bset(s, t), Z.data(), nn * sizeof(cd), cudaMemcpyHostToDevice));
+      }
     }
   }
   int dummy = 0;

@@ -112,7 +112,15 @@ struct Ctrl {
   int conv[kMaxShifts];            // shift converged in the current iteration
   double resid_shift[kMaxShifts];  // last shifted residual estimate
   double sigma[kMaxShifts];
-  int n_act[2];                    // n_unconv of the last odd / even iteration ([iter & 1]; paired multishift update)
+  int n_act[4];                    // n_unconv of the last iterations ([iter % ring]; deferred multishift updates)
+  // ---- overlapped multishift update (schedule 3 with BCG_OVERLAP): the shifted systems are updated by a launch
+  // that runs BESIDE the next iterations' kernels, so it reads the state of ITS iteration from a snapshot the
+  // B-step leaves in slot [iter & 1] (the loop's own fields above have moved on by then) ----
+  struct Snap {
+    int iter, stop, n_now;
+    int n_ring[4];
+  } snap[2];
+  int bulk_served[2];              // snap[p].iter of the last launch that served slot p (a later one is a no-op)
   // ---- statistics of the solve (read back by bcg_last_solve_stats; nothing in the loop depends on them) ----
   unsigned hist[kMaxShifts + 1];       // hist[a] = iterations that ran with a systems still being updated
   unsigned long long shift_passes;     // field-sized passes (units of F = 48 N V bytes) the multishift update has moved
@@ -204,6 +212,75 @@ __host__ __device__ inline int build_shift_items(int schedule, int iter, int sto
   }
 #undef BCG_ADD_ITEM
   if (passes) *passes = qpasses + 4 * systems;
+  return n;
+}
+
+// ---- schedule 3: staggered deferral of depth k (2 <= k <= ring <= kMaxDepth), streamed operands ---------------
+// System s >= 1 is served in the iterations i with i % k == s % k and then receives the updates of the k
+// iterations (i-k, i] in order, each with the coefficients and the Q of its own iteration (Q lives in a ring of
+// `ring` >= k fields: Q -= T alpha of iteration i reads field (i-1) % ring and writes field i % ring, so the last
+// `ring` are intact).  X_s, P_s are read and written once per k iterations: (7 + (k-1) + 4 (S_act-1)/k) F per
+// iteration, balanced launch by launch.  A system that retired keeps only the updates of the iterations in which
+// it was active; the iteration the loop ends on flushes everything that is pending.  k = 2 is schedule 2.
+// `part`: 0 the whole launch ; 1 the critical part only (Q <- Q rho^-1 and system 0: what the next stencil waits
+// for) ; 2 the shifted systems only, every Q read from the ring (the launch that overlaps the next iterations,
+// ring = k + 1: the fields and operand sets of the last k iterations then survive one more iteration).
+constexpr int kMaxDepth = 4;
+struct StagItem {
+  signed char kind;     // KQ: Q <- Q rho^-1 ; KCUR: system s gets m updates
+  signed char s;
+  signed char d_first;  // its first pending update is that of iteration iter - d_first
+  signed char m;        // number of pending updates (consecutive iterations from there)
+};
+// n_ring[j % ring] = systems active in iteration j for the previous k-1 iterations; n_now: in this one.
+// *passes = field-sized passes through HBM (Q in / out, every distinct Q read from the ring once, 4 per system served).
+__host__ __device__ inline int build_stag_items(int k, int ring, int part, int iter, int stop, int n_now,
+                                                const int* n_ring, StagItem* out, int* passes) {
+  int n = 0, systems = 0;
+  unsigned hist_mask = 0;
+  if (part != 2) {
+    if (out) {
+      out[0].kind = KQ; out[0].s = -1; out[0].d_first = 0; out[0].m = 0;
+      out[1].kind = KCUR; out[1].s = 0; out[1].d_first = 0; out[1].m = 1;
+    }
+    n = 2;
+    systems = 1;
+  }
+  int top = n_now;  // no system beyond the largest active count of the last k iterations has anything pending
+  for (int t = 0; t < ring; ++t) top = n_ring[t] > top ? n_ring[t] : top;
+  if (top > kMaxShifts) top = kMaxShifts;
+  for (int s = 1; s < top && part != 1; ++s) {
+    const bool mine = (s % k) == (iter % k);
+    if (!mine && !stop) continue;
+    int first;
+    if (mine) {
+      first = iter - k + 1;
+    } else {
+      int back = (iter - s) % k;  // iterations since this system's group was served last
+      if (back < 0) back += k;
+      first = iter - back + 1;
+    }
+    if (first < 1) first = 1;
+    int m = 0;
+    for (int j = first; j <= iter; ++j) {
+      const int na = (j == iter) ? n_now : n_ring[j % ring];
+      if (s < na) ++m; else break;  // retirement is permanent: the active iterations are a prefix
+    }
+    if (m == 0) continue;
+    if (out) {
+      out[n].kind = KCUR;
+      out[n].s = static_cast<signed char>(s);
+      out[n].d_first = static_cast<signed char>(iter - first);
+      out[n].m = static_cast<signed char>(m);
+    }
+    for (int u = 0; u < m; ++u)
+      if (iter - first - u > 0 || part == 2) hist_mask |= 1u << (iter - first - u);
+    ++n;
+    ++systems;
+  }
+  int hist = 0;
+  for (int d = 0; d < kMaxDepth; ++d) hist += (hist_mask >> d) & 1u;
+  if (passes) *passes = (part != 2 ? 2 : 0) + hist + 4 * systems;
   return n;
 }
 
@@ -309,6 +386,10 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // make generic-proxy smem writes visible to the async proxy (before a bulk store)
+// named barrier `id` (1..15) among `nthreads` threads of the CTA (a multiple of 32; whole warps take part)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG / UTMASTG) ----------------------------

@@ -8,8 +8,10 @@
 #include "dirac_chain.cuh"
 #include "axpy_pipe.cuh"
 #include "dirac4d.cuh"
+#include "dirac4_tile.cuh"
 #include "shift_pair.cuh"
 #include "shift_dmma.cuh"
+#include "shift_stag.cuh"
 
 namespace bcg {
 
@@ -31,6 +33,13 @@ struct OpsTable {
   int (*dirac4_sweep)(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* U, const Lattice4* lat,
                       long long x_begin, long long x_end, double m2, double sigma, int second, const Ctrl* ctrl,
                       int* launches);
+  // the same sweep, second generation (dirac4_tile.cuh): rows [row_begin, row_end) of the local lattice (row = L0
+  // consecutive sites), Ut = direction-major links.  gpart != nullptr (second sweep only): every CTA also leaves its
+  // partial Gram p0^dag out -- returns their number; otherwise 0; < 0: error (-cudaErrorNotSupported: the lattice
+  // row does not fit a tile, use dirac4_sweep).  nullptr where the kernel does not fit the SM at this N.
+  int (*dirac4_tile)(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* Ut, const Lattice4* lat,
+                     long long site_stride_mu, long long row_begin, long long row_end, double m2, double sigma, int second,
+                     cd* gpart, const Ctrl* ctrl, int sms, int* launches);
   int (*gram)(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
               int* launches);
   // Q += T*M (+ Gram of the result); Qout != nullptr: the result goes to Qout, Q is left untouched
@@ -62,6 +71,13 @@ struct OpsTable {
   int (*shift_update_dmma)(cudaStream_t st, cd* Q, cd* Qprev, const ShiftPtrs* fp, const cd* Rm, const cd* A_odd,
                            const cd* B_odd, const cd* A_even, const cd* B_even, long long V, const Ctrl* ctrl,
                            int sms, int* launches, int schedule, cd* p0_halo, const HaloFold* hf);
+  // the same update with the shifted systems served once per `depth` iterations (schedule 3, shift_stag.cuh):
+  // Qring[t] = the Q field of the iterations with i % depth == t, coefs = the operand sets likewise
+  // ring = fields / operand sets in use (>= depth), part = 0 whole launch / 1 Q and system 0 / 2 shifted systems
+  // from the snapshot `slot`, max_ctas > 0 caps the grid (build_stag_items, shift_stag_kernel)
+  int (*shift_update_stag)(cudaStream_t st, cd* const* Qring, int depth, int ring, int part, int slot, int max_ctas,
+                           const ShiftPtrs* fp, const cd* Rm, const ShiftStagCoefs* coefs, long long V, const Ctrl* ctrl,
+                           int sms, int* launches, cd* p0_halo, const HaloFold* hf);
   int (*max_partials)(int sms);
   // sites that must be allocated after site 0 of every field / of the links (>= V + 2): the
   // tensor-map views of the chain stencil are rectangular and reach past the end of the field
@@ -214,7 +230,7 @@ struct Ops {
   // resident-CTA capacities (CTAs per SM x SMs), filled once by prepare() --
   // outside any stream capture -- and used to size the persistent grids.
   struct Caps {
-    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0, dmma = 0, dmma1 = 0, dmma2 = 0;
+    int dirac_g = 0, dirac = 0, gram = 0, axpy_g = 0, axpy = 0, rescale = 0, trsm = 0, shift = 0, pipe = 0, pair = 0, dmma = 0, dmma1 = 0, dmma2 = 0, stag = 0;
   };
   // Both the shared-memory opt-ins (cudaFuncSetAttribute) and the occupancy figures are per
   // DEVICE: one slot per device ordinal, filled under a lock the first time a context of that
@@ -245,6 +261,7 @@ struct Ops {
     if constexpr (PAIR_OK) c.pair = occupancy_blocks(shift_pair_kernel<N, SHIFT_TS>, SG::NT, SPG::SMEM_BYTES, sms);
     if constexpr (DMMA_OK) c.dmma = occupancy_blocks(shift_dmma_kernel<N, SHIFT_TS, 2>, SDG::NT, SDG::SMEM_BYTES, sms);
     if constexpr (DMMA_CFG1) c.dmma1 = occupancy_blocks(shift_dmma_kernel<N, 32, 3>, SDG1::NT, SDG1::SMEM_BYTES, sms);
+    if constexpr (STAG_OK) c.stag = occupancy_blocks(shift_stag_kernel<N, SHIFT_TS>, SSG::NT, SSG::SMEM_BYTES, sms);
     if constexpr (DMMA_CFG2) c.dmma2 = occupancy_blocks(shift_dmma_kernel<N, 64, 2>, SDG2::NT, SDG2::SMEM_BYTES, sms);
     if constexpr (APIPE) {
       if constexpr (DFMA_GRAM)
@@ -255,6 +272,12 @@ struct Ops {
       if constexpr (N % 4 == 0)
         cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)APG::SMEM_BYTES);
+    }
+    if constexpr (D4::OK) {
+      cudaFuncSetAttribute(dirac4_tile_kernel<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D4::SMEM_BYTES);
+      cudaFuncSetAttribute(dirac4_tile_kernel<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D4::SMEM_BYTES);
+      if constexpr (D4::CAN_GRAM)
+        cudaFuncSetAttribute(dirac4_tile_kernel<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D4::SMEM_BYTES);
     }
     if constexpr (CHAIN) {
       if constexpr (DFMA_GRAM)
@@ -323,6 +346,35 @@ struct Ops {
     }
     if (launches) ++*launches;
     return err();
+  }
+
+  using D4 = Dirac4TileGeom<N>;
+  static int dirac4_tile(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* Ut, const Lattice4* lat,
+                         long long site_stride_mu, long long row_begin, long long row_end, double m2, double sigma, int second,
+                         cd* gpart, const Ctrl* ctrl, int sms, int* launches) {
+    if constexpr (D4::OK) {
+      if (row_end <= row_begin) return 0;
+      if (static_cast<long long>(lat->L0) * D4::G > D4::NTC) return -static_cast<int>(cudaErrorNotSupported);
+      if (gpart != nullptr && (!D4::CAN_GRAM || !second)) return -static_cast<int>(cudaErrorNotSupported);
+      prepare(sms);
+      const int b = D4::NTC / (D4::G * lat->L0);  // rows per tile
+      const long long ntiles = (row_end - row_begin + b - 1) / b;
+      const int grid = clamp_grid(ntiles, sms);   // one persistent CTA per SM
+      const Rows4 geo = {lat->L0, lat->L1, lat->L2, lat->L3, site_stride_mu};
+      if (!second)
+        dirac4_tile_kernel<N, false, false><<<grid, D4::NT, D4::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end, b, m2,
+                                                                                   sigma, nullptr, ctrl);
+      else if (gpart == nullptr)
+        dirac4_tile_kernel<N, true, false><<<grid, D4::NT, D4::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end, b, m2,
+                                                                                  sigma, nullptr, ctrl);
+      else if constexpr (D4::CAN_GRAM)
+        dirac4_tile_kernel<N, true, true><<<grid, D4::NT, D4::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end, b, m2,
+                                                                                 sigma, gpart, ctrl);
+      if (launches) ++*launches;
+      const int e = err();
+      return e ? e : (gpart != nullptr ? grid : 0);
+    }
+    return -static_cast<int>(cudaErrorNotSupported);
   }
 
   static int gram(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
@@ -576,6 +628,44 @@ struct Ops {
     return -static_cast<int>(cudaErrorNotSupported);
   }
 
+  using SSG = ShiftStagGeom<DMMA_N ? N : 4, SHIFT_TS>;
+  static constexpr bool STAG_OK = DMMA_OK && SSG::SMEM_BYTES <= 227 * 1024;
+  static int shift_update_stag(cudaStream_t st, cd* const* Qring, int depth, int ring, int part, int slot, int max_ctas,
+                               const ShiftPtrs* fp, const cd* Rm, const ShiftStagCoefs* coefs, long long V, const Ctrl* ctrl,
+                               int sms, int* launches, cd* p0_halo, const HaloFold* hfp) {
+    if constexpr (STAG_OK) {
+      prepare(sms);
+      HaloFold hf;
+      if (hfp) hf = *hfp; else std::memset(&hf, 0, sizeof hf);
+      int grid = clamp_grid((V + SHIFT_TS - 1) / SHIFT_TS, caps().stag);
+      if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+      alignas(64) ShiftStagMaps maps;
+      const long long npairs = (V + 1) / 2;
+      int e = 0;
+      for (int t = 0; t < kMaxDepth && !e; ++t)
+        e = make_pair_map(&maps.Q[t], Qring[t < ring ? t : 0], 3 * N, SSG::PAIR, npairs, SHIFT_TS / 2);
+      for (int s = 0; s < kMaxShifts && !e; ++s) {
+        if (fp->P[s] == nullptr || fp->X[s] == nullptr) {
+          maps.P[s] = maps.Q[0];  // never used: the device loop stops at the active count
+          maps.X[s] = maps.Q[0];
+          continue;
+        }
+        e = make_pair_map(&maps.P[s], fp->P[s], 3 * N, SSG::PAIR, npairs, SHIFT_TS / 2);
+        if (!e) e = make_pair_map(&maps.X[s], fp->X[s], 3 * N, SSG::PAIR, npairs, SHIFT_TS / 2);
+      }
+      if (e) return e;
+      launch_pdl(shift_stag_kernel<N, SHIFT_TS>, grid, SSG::NT, SSG::SMEM_BYTES, st, maps, Rm, *coefs, V, ctrl, depth, ring, part,
+                 slot, p0_halo, hf);
+      if (launches) ++*launches;
+      if (part == 2) {
+        bulk_mark_kernel<<<1, 1, 0, st>>>(const_cast<Ctrl*>(ctrl), slot);
+        if (launches) ++*launches;
+      }
+      return err();
+    }
+    return -static_cast<int>(cudaErrorNotSupported);
+  }
+
   static int shift_update_direct(cudaStream_t st, cd* Q, const ShiftPtrs* fp, const cd* Rm, const cd* A,
                                  const cd* B, long long V, int do_backsub, int n_active_fixed, const Ctrl* ctrl,
                                  int sms, int* launches) {
@@ -599,6 +689,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::dirac,
                              &Ops<N>::dirac_v1,
                              &Ops<N>::dirac4_sweep,
+                             Ops<N>::D4::OK ? &Ops<N>::dirac4_tile : nullptr,
                              &Ops<N>::gram,
                              &Ops<N>::axpy_gram,
                              Ops<N>::APIPE ? 1 : 0,
@@ -610,6 +701,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::shift_update_direct,
                              Ops<N>::PAIR_OK ? &Ops<N>::shift_update_pair : nullptr,
                              Ops<N>::DMMA_OK ? &Ops<N>::shift_update_dmma : nullptr,
+                             Ops<N>::STAG_OK ? &Ops<N>::shift_update_stag : nullptr,
                              &Ops<N>::max_partials,
                              &Ops<N>::field_capacity,
                              &Ops<N>::prepare};

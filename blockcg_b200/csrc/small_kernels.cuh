@@ -39,10 +39,19 @@ struct MatLayout {
   __host__ __device__ size_t beta_s(int s) const { return (M_FIXED_COUNT + 3 * S + s) * nn(); }
   // paired multishift update (shift_pair.cuh): the operands of odd iterations live in a second set of
   // slots, so that the even iteration's launch still finds them
-  int pair = 0;  // schedule of the multishift update: 0 plain, 1 alternating, 2 staggered (build_shift_items)
-  __host__ __device__ size_t A(int s, int iter) const { return ((pair && (iter & 1)) ? M_FIXED_COUNT + 4 * S + s : M_FIXED_COUNT + s) * nn(); }
-  __host__ __device__ size_t B(int s, int iter) const { return ((pair && (iter & 1)) ? M_FIXED_COUNT + 5 * S + s : M_FIXED_COUNT + S + s) * nn(); }
-  __host__ __device__ size_t total() const { return (M_FIXED_COUNT + 6 * S) * nn(); }
+  int pair = 0;   // schedule of the multishift update: 0 plain, 1 alternating, 2 staggered (build_shift_items),
+                  // 3 staggered of depth `depth` with streamed operands (build_stag_items)
+  int depth = 2;  // deferral depth k of the schedules 1..3
+  int ring = 2;   // operand sets / Q fields / n_act slots in use: those of iteration i are number i % ring
+                  // (= depth, or depth + 1 when the shifted systems' launch overlaps the next iterations)
+  int overlap = 0;
+  // operand set t of [A[S], B[S]]: set 0 at the historical place, sets 1 .. kMaxDepth-1 behind alpha_s / beta_s
+  __host__ __device__ size_t Aset(int s, int t) const { return (t == 0 ? M_FIXED_COUNT + s : M_FIXED_COUNT + 4 * S + 2 * S * (t - 1) + s) * nn(); }
+  __host__ __device__ size_t Bset(int s, int t) const { return (t == 0 ? M_FIXED_COUNT + S + s : M_FIXED_COUNT + 4 * S + 2 * S * (t - 1) + S + s) * nn(); }
+  __host__ __device__ int set_of(int iter) const { return pair ? iter % ring : 0; }
+  __host__ __device__ size_t A(int s, int iter) const { return Aset(s, set_of(iter)); }
+  __host__ __device__ size_t B(int s, int iter) const { return Bset(s, set_of(iter)); }
+  __host__ __device__ size_t total() const { return (M_FIXED_COUNT + 4 * S + 2 * S * (kMaxDepth - 1)) * nn(); }
 };
 
 // (row, column) of every linear matrix index, filled once per kernel: an integer division by
@@ -737,7 +746,7 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
       // the copies the next A-step reads (its CTAs must not race with CTA 0's own updates)
       ctrl->iter_b = iter;
       ctrl->n_unconv_b = ctrl->n_unconv;
-      ctrl->n_act[iter & 1] = ctrl->n_unconv;
+      ctrl->n_act[L.set_of(iter)] = ctrl->n_unconv;
       // while (residual > eps && iter < max_iterations)  -- NaN ends the loop as in the reference
       int stop = 0;
       if (!(r > ctrl->eps) || iter >= ctrl->max_it) stop = 1;
@@ -752,7 +761,28 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
       const int na = ctrl->n_unconv;
       ctrl->hist[na < 0 ? 0 : (na > kMaxShifts ? kMaxShifts : na)] += 1u;
       int passes = 0;
-      build_shift_items(L.pair, iter, stop, na, ctrl->n_act[(iter - 1) & 1], nullptr, &passes);
+      if (L.pair == 3) {
+        int ring[kMaxDepth];
+        for (int t = 0; t < kMaxDepth; ++t) ring[t] = ctrl->n_act[t];
+        if (L.overlap) {
+          // the launch that serves the shifted systems runs beside the next iterations: leave it this
+          // iteration's state (the slot is free again: the launch that read it two iterations ago has been
+          // joined before this iteration's Q update)
+          Ctrl::Snap& sn = ctrl->snap[iter & 1];
+          sn.stop = stop;
+          sn.n_now = na;
+          for (int t = 0; t < kMaxDepth; ++t) sn.n_ring[t] = ring[t];
+          sn.iter = iter;
+          int p2 = 0;
+          build_stag_items(L.depth, L.ring, 1, iter, stop, na, ring, nullptr, &passes);
+          build_stag_items(L.depth, L.ring, 2, iter, stop, na, ring, nullptr, &p2);
+          passes += p2;
+        } else {
+          build_stag_items(L.depth, L.ring, 0, iter, stop, na, ring, nullptr, &passes);
+        }
+      } else {
+        build_shift_items(L.pair, iter, stop, na, ctrl->n_act[(iter - 1) & 1], nullptr, &passes);
+      }
       ctrl->shift_passes += static_cast<unsigned long long>(passes);
     }
     return;

@@ -180,7 +180,10 @@ int bcg_solve_scg(bcg_ctx* ctx, double* const* x_host, const double* b_host, con
 typedef struct {
   int iterations;
   int n_shifts;
-  int paired;                                    /* 1: shifted systems were served every second iteration */
+  int paired;                                    /* schedule of the multishift update (bcg_shift_schedule /
+                                                    bcg_stag_schedule): 0 every system every iteration, 1 / 2 the
+                                                    shifted systems every second iteration, 3 every depth-th */
+  int depth;                                     /* deferral depth of that schedule (1 for schedule 0) */
   uint32_t active_hist[BCG_MAX_SHIFTS + 1];      /* [a] = iterations in which a systems were still updated
                                                     (block_solvers.hpp:161,179-181: shifts retire at eps_shifts) */
   uint64_t shift_update_field_passes;            /* field-sized (48 N V bytes) reads + writes the multishift
@@ -199,6 +202,18 @@ int bcg_last_solve_stats(bcg_ctx* ctx, bcg_solve_stats* out);
  * iterations' updates.  Returns the number of items (<= BCG_MAX_SHIFTS + 2). */
 int bcg_shift_schedule(int schedule, int iteration, int stop, int n_active, int n_active_prev, int* kinds, int* systems,
                        int* field_passes);
+
+/* Schedule 3 (BCG_PAIR=3, deferral depth BCG_DEPTH = 2..4): system s >= 1 is served in the iterations i with
+ * i % depth == s % depth and then receives its (up to) `depth` pending updates in iteration order, each with the
+ * coefficients and the Q of its own iteration (Q lives in a ring of `ring` >= depth fields), so the bits are again
+ * those of the plain loop (block_solvers.hpp:161-182).  n_active_ring[j % ring] = systems active in iteration j, for
+ * the depth-1 iterations before `iteration`.  part = 0: the whole launch; with BCG_OVERLAP=1 the launch is split into
+ * part 1 (Q <- Q rho^-1 and system 0, on the loop's stream) and part 2 (the shifted systems, ring = depth + 1, on a
+ * second stream beside the next iterations' kernels).  Per item i: systems[i] (-1 = the Q item), first_back[i] (its
+ * first pending update is that of iteration `iteration - first_back[i]`), n_updates[i].  Returns the number of items
+ * (-1: bad argument). */
+int bcg_stag_schedule(int depth, int ring, int part, int iteration, int stop, int n_active, const int* n_active_ring,
+                      int* systems, int* first_back, int* n_updates, int* field_passes);
 
 /* In-loop profile: n_iterations (<= 4096) of the NEXT solve on this context, starting once at least
  * after_iterations have run (so the GPU is at its sustained clocks), are submitted kernel by kernel with a

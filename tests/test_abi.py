@@ -145,3 +145,55 @@ def test_update_schedules_apply_every_update_once_and_in_order():
                 plain = total
             else:
                 assert total <= plain + 2 * n_it   # deferring never moves more than the plain loop (+ the kept Q)
+
+
+def test_deep_staggered_schedule_applies_every_update_once_and_in_order():
+    """Schedule 3 (bcg_stag_schedule = build_stag_items, the function shift_stag_kernel and the B-step evaluate):
+    simulated solves with random retirements (highest system first, block_solvers.hpp:161,179-181) and stopping
+    points, deferral depths 2, 3, 4.  Every system receives the update of every iteration in which it was active
+    exactly once and in order; an update older than `depth - 1` iterations is never requested (its Q field would
+    have been overwritten); system 0 and the Q item come first in every launch; the byte accounting matches."""
+    import random
+
+    from blockcg_b200.capi import stag_schedule
+    rng = random.Random(11)
+    for trial in range(300):
+        S = rng.randint(1, 9)
+        n_it = rng.randint(1, 40)
+        act, a = [], S
+        for i in range(n_it):
+            act.append(a)
+            if a > 1 and rng.random() < 0.15:
+                a -= rng.randint(1, min(2, a - 1))
+        want = {s: [i + 1 for i in range(n_it) if s < act[i]] for s in range(S)}
+        plain = sum(2 + 4 * act[i] for i in range(n_it))
+        for depth, overlap in ((2, 0), (3, 0), (4, 0), (2, 1), (3, 1)):
+            R = depth + overlap   # ring of Q fields / operand sets (one more when the launch overlaps the next iterations)
+            got = {s: [] for s in range(S)}
+            ring = [0, 0, 0, 0]
+            total = 0
+            for i in range(1, n_it + 1):
+                if overlap:   # the two launches of the overlapped variant together do what the whole launch does
+                    crit, p1 = stag_schedule(depth, i, i == n_it, act[i - 1], ring, R, 1)
+                    bulk, p2 = stag_schedule(depth, i, i == n_it, act[i - 1], ring, R, 2)
+                    assert crit == [(-1, 0, 0), (0, 0, 1)] and p1 == 6
+                    assert all(s >= 1 for s, _, _ in bulk)
+                    items, passes = crit + bulk, p1 + p2
+                else:
+                    items, passes = stag_schedule(depth, i, i == n_it, act[i - 1], ring)
+                assert items[0] == (-1, 0, 0) and items[1] == (0, 0, 1)
+                earlier = set()
+                for s, first_back, m in items[1:]:
+                    assert 0 <= first_back <= depth - 1 and 1 <= m <= first_back + 1
+                    if s >= 1 and i != n_it:
+                        assert s % depth == i % depth
+                    for u in range(m):
+                        got[s].append(i - first_back + u)
+                        if first_back - u > 0 or (overlap and s >= 1):   # overlapped: every Q comes from the ring
+                            earlier.add(first_back - u)
+                assert len({s for s, _, _ in items}) == len(items)
+                assert passes == 2 + len(earlier) + 4 * (len(items) - 1)
+                total += passes
+                ring[i % R] = act[i - 1]
+            assert got == want, (depth, overlap, S, act, got, want)
+            assert total <= plain + depth * n_it

@@ -228,6 +228,41 @@ def test_4d_extension(bcg, oracle, dims, N):
         oracle.set_lattice(None)
 
 
+@pytest.mark.parametrize("dims,N", [((24, 3, 1, 3), 12), ((6, 5, 7, 3), 12), ((4, 4, 4, 4), 8), ((5, 1, 3, 4), 3),
+                                    ((1, 2, 3, 4), 4), ((2, 1, 1, 1), 16), ((3, 2, 2, 2), 32), ((70, 1, 2, 2), 12)])
+def test_4d_tiled_sweep_matches_gather_kernel(bcg, oracle, dims, N, monkeypatch):
+    """Second-generation 4-D sweep (dirac4_tile.cuh: rows streamed through shared memory, direction-major links)
+    against the first one (dirac4d.cuh, neighbours gathered from global memory): the same operations in the same
+    order, so the operator's output agrees bit for bit -- tiles that end in the middle of the row list, extents 1
+    and 2, a row too long for a tile (falls back to the gather kernel) -- and both agree with the CPU restatement
+    (parity UNPINNED: the reference has no 4-D operator).  The Gram fused into the second sweep sums per tile
+    instead of per 32 sites: equal to rounding."""
+    rng = np.random.default_rng(sum(dims) * 7 + N)
+    V = int(np.prod(dims))
+    U = rng.uniform(-1, 1, (V, 4, 3, 3)) + 1j * rng.uniform(-1, 1, (V, 4, 3, 3))
+    B = rng.uniform(-1, 1, (V, N, 3)) + 1j * rng.uniform(-1, 1, (V, N, 3))
+    mass = 0.3
+    oracle.set_lattice(dims)
+    try:
+        got = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("BCG_DIRAC4_TILE", mode)
+            with bcg.Context(V, N, dims=dims) as ctx:
+                ctx.set_links(U, mass)
+                hb, ha, hc = ctx.field(B), ctx.field(), ctx.field()
+                G = ctx.op(ha, hb, sigma=0.25, want_gram=True)
+                ctx.op(hc, ha)            # a second application, no Gram, sigma = 0
+                got[mode] = (G, ctx.download(ha), ctx.download(hc))
+        assert np.array_equal(got["1"][1], got["0"][1])
+        assert np.array_equal(got["1"][2], got["0"][2])
+        assert rel(got["1"][0], got["0"][0]) < 1e-13
+        AB = oracle.op(U, B, mass, 0.25)
+        assert rel(got["1"][1], AB) < 1e-13
+        assert rel(got["1"][0], oracle.hermitian_dot(B, AB)) < 1e-12
+    finally:
+        oracle.set_lattice(None)
+
+
 def test_full_size_properties(bcg, oracle):
     """BASELINE config sizes (16^4, N=12): properties that need no CPU solve."""
     V, N, mass = 16 ** 4, 12, 1e-3
@@ -290,16 +325,25 @@ def test_paired_multishift_update_is_bit_identical(bcg, oracle, V, N, max_it, ep
     shifts = [0.0, 1e-4, 1e-2, 0.1, 0.5, 0.9]
     U, B = oracle.make_inputs(V, N, 5)
     out = {}
-    for mode in ("0", "1", "2"):   # plain, alternating, staggered schedule (build_shift_items)
-        monkeypatch.setenv("BCG_PAIR", mode)
+    # plain, alternating, staggered schedule (build_shift_items); staggered of depth 3 and 4 (build_stag_items);
+    # the same with the shifted systems' launch on a second stream beside the next iterations (BCG_OVERLAP)
+    modes = {"0": {"BCG_PAIR": "0"}, "1": {"BCG_PAIR": "1"}, "2": {"BCG_PAIR": "2"},
+             "3/3": {"BCG_PAIR": "3", "BCG_DEPTH": "3"}, "3/4": {"BCG_PAIR": "3", "BCG_DEPTH": "4"},
+             "3/2/overlap": {"BCG_PAIR": "3", "BCG_DEPTH": "2", "BCG_OVERLAP": "1"},
+             "3/3/overlap": {"BCG_PAIR": "3", "BCG_DEPTH": "3", "BCG_OVERLAP": "1", "BCG_BULK_CTAS": "37"}}
+    for mode, env in modes.items():
+        for k in ("BCG_PAIR", "BCG_DEPTH", "BCG_OVERLAP", "BCG_BULK_CTAS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         with bcg.Context(V, N, max_shifts=len(shifts)) as ctx:
             ctx.set_links(U, mass)
             hb = ctx.field(B)
             xs = [ctx.field() for _ in shifts]
             info = ctx.solve_sbcgrq_dev(xs, hb, shifts, eps, eps_shifts, max_it)
             out[mode] = (info.iterations, info.n_unconverged, [ctx.download(h) for h in xs])
-    for mode in ("1", "2"):
-        assert out["0"][0] == out[mode][0] and out["0"][1] == out[mode][1]
+    for mode in modes:
+        assert out["0"][0] == out[mode][0] and out["0"][1] == out[mode][1], mode
         for a, b in zip(out["0"][2], out[mode][2]):
             assert np.array_equal(a, b), mode
     if max_it > 1000:
@@ -496,7 +540,7 @@ def test_solve_statistics(bcg, oracle):
     V, N, mass, eps = 1000, 12, 0.02, 1e-10
     shifts = [0.0, 1e-4, 1e-2, 0.1, 0.5, 0.9]
     U, B = oracle.make_inputs(V, N, 5)
-    for pair in ("0", "1", "2"):
+    for pair in ("0", "1", "2", "3"):
         os.environ["BCG_PAIR"] = pair
         try:
             with bcg.Context(V, N, max_shifts=len(shifts)) as ctx:
@@ -515,7 +559,7 @@ def test_solve_statistics(bcg, oracle):
         if pair == "0":
             assert st["shift_update_field_passes"] == plain
         else:   # shifted systems touched once per two iterations: fewer passes than the plain loop
-            assert 0.5 * plain < st["shift_update_field_passes"] < plain
+            assert 0.4 * plain < st["shift_update_field_passes"] < plain
         assert st["resid_shift"][0] == info.residual
 
 
