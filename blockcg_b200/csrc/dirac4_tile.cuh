@@ -6,20 +6,26 @@
 //
 // The first version gathered every neighbour and every link straight from global memory, one thread per (site,
 // right-hand side): 96 16-byte loads per thread and sweep, three quarters of them re-reading the same 3x3 link in all
-// N threads of a site -- bound by L1 wavefronts (ncu-free estimate 445 us, measured 508 us per apply at 24^4, N = 12).
+// N threads of a site -- bound by L1 wavefronts (508 us per apply at 24^4, N = 12).
 // Here nothing is gathered.  The unit of data movement is one x0-ROW of the lattice (L0 consecutive sites: L0 * 48N
 // contiguous bytes of a field, L0 * 144 contiguous bytes of one direction's links, which are kept direction-major
-// for that purpose: Ut[mu][site][3][3]).  A CTA owns a tile of b consecutive rows.  For every one of the eight
-// directions the neighbour sites of the tile are again whole rows (the same rows for +-x0, rows with x1, x2 or x3
-// stepped -- periodically, or into the x3 halo slices -- for the others), so a producer lane streams, stage by
-// stage, [neighbour rows of the field | the rows of U_mu that direction needs] into a shared-memory ring with bulk
-// copies, and the compute threads -- (site, R right-hand sides), 6R accumulators in registers for the whole tile --
-// consume the stages in the order mu = 0+, 0-, 1+, 1-, ... of the first version, so the results are bit-identical
-// to it.  The result tile goes back through shared memory and one bulk store; the second sweep takes P itself as a
-// ninth stage for the mass term and can accumulate the Gram P^dag T of the tile on the way (GramCta), which saves
-// the stand-alone Gram kernel's two field reads.  Per site and sweep a CTA reads 7 (8) x 48N + 8 x 144 bytes from
-// L2 and 5.6 shared-memory wavefronts per site and direction against 6.75 FP64-pipe cycles: the kernel is meant to
-// sit on the FP64 pipe and the L2 -> SM path at once, not on L1.
+// for that purpose: Ut[mu][site][3][3]).  A CTA owns a tile of b consecutive rows (b = 1 for the shapes the launcher
+// picks).  For every one of the eight directions the neighbour sites of the tile are again whole rows (the same rows
+// for +-x0, rows with x1, x2 or x3 stepped -- periodically, or into the x3 halo slices -- for the others), so a
+// producer lane streams, stage by stage, [neighbour rows of the field | the rows of U_mu that direction needs] into a
+// shared-memory ring with bulk copies, and the compute threads -- (site, R right-hand sides), 6R accumulators in
+// registers for the whole tile -- consume the stages in the order mu = 0+, 0-, 1+, 1-, ... of the first version, so
+// the results are bit-identical to it.  The result tile goes back through shared memory and one bulk store; the
+// second sweep takes P itself as a last stage for the mass term and, where the shape has enough warps for it,
+// accumulates the Gram P^dag T of the tile on the way (GramCta).
+//
+// What bounds it (ncu, profiles/r02_ncu_dirac4_tile.txt): nothing is saturated -- FP64 pipe 28 %, L2 30 %, DRAM 29 %
+// with one 6-warp CTA per SM and a four-stage ring; the compute warps wait for row deliveries (7 x 48N + 8 x 144
+// bytes per site and sweep come from L2: every field row is fetched by the seven tiles that touch it).  Independent
+// pipelines hide that latency better than a deeper ring: 24^4, N = 12, per apply (two sweeps) 518 us with one 6-warp
+// CTA per SM, 397 us with two, 331 us with four 3-warp CTAs (one row each, two stages) -- the shape the launcher
+// therefore picks (ops.cuh: the smallest CTA whose tile holds one row).  Cutting the seven fetches per row needs tiles
+// that are blocks in x1, x2 (and a sliding window in x3); with 13.8 KB per row that does not fit beside the ring.
 #pragma once
 #include "common.cuh"
 #include "field_kernels.cuh"
@@ -27,22 +33,29 @@
 
 namespace bcg {
 
-template <int N>
+// NCW_ compute warps + one producer warp: the launcher picks, among the shapes compiled in, the one whose
+// tile (whole rows, one thread per site and R right-hand sides) leaves the fewest threads idle at this L0
+template <int N, int NCW_, int NSMAX = 2>
 struct Dirac4TileGeom {
   static constexpr int R = (N % 3 == 0) ? 3 : (N % 2 == 0) ? 2 : 1;  // right-hand sides per thread
   static constexpr int G = N / R;                                      // threads per site
-  static constexpr int NCW = 8, NTC = NCW * 32, NT = NTC + 32;        // compute warps + one producer warp
+  static constexpr int NCW = NCW_, NTC = NCW * 32, NT = NTC + 32;
   static constexpr int TSMAX = NTC / G;                                // sites per tile at most
   static constexpr int SITE = 3 * N;
   static constexpr int STAGE_ELEMS = TSMAX * (SITE + 9);              // [field rows | link rows]
   static constexpr int OUT_ELEMS = TSMAX * SITE;
-  static constexpr bool CAN_GRAM = NCW >= GramGeom<N>::NTASK;
+  // the Gram of the tile on the way: only where it costs few registers (N <= 4: one 4x4 block per warp) -- at N = 8 the
+  // fused sweep measured slower than the plain sweep + the stand-alone Gram kernel (384 vs 349 us at 24^4)
+  static constexpr bool CAN_GRAM = NCW >= GramGeom<N>::NTASK && N <= 4;
   static constexpr int GRAM_ELEMS = CAN_GRAM ? (NCW / GramGeom<N>::NTASK) * N * N : 0;
   static constexpr size_t FIXED_BYTES = sizeof(cd) * (OUT_ELEMS + GRAM_ELEMS) + 128;
-  static constexpr int NSTAGE = (227 * 1024 - static_cast<int>(FIXED_BYTES)) / static_cast<int>(sizeof(cd) * STAGE_ELEMS) >= 4
-                                    ? 4 : (227 * 1024 - static_cast<int>(FIXED_BYTES)) / static_cast<int>(sizeof(cd) * STAGE_ELEMS);
-  static constexpr bool OK = NSTAGE >= 2 && TSMAX >= 1;
+  static constexpr int NSFIT = (227 * 1024 - static_cast<int>(FIXED_BYTES)) / static_cast<int>(sizeof(cd) * STAGE_ELEMS);
+  static constexpr int NSTAGE = NSFIT >= NSMAX ? NSMAX : NSFIT;  // NSMAX = 2: a ring short enough for two CTAs per SM
+  static constexpr bool OK = NSTAGE >= 2 && TSMAX >= 1 && NT <= 1024;
   static constexpr size_t SMEM_BYTES = sizeof(cd) * (NSTAGE * STAGE_ELEMS) + FIXED_BYTES;
+  static constexpr int CTAS_SMEM = static_cast<int>((227 * 1024) / (SMEM_BYTES + 1024));
+  static constexpr int CTAS_THREADS = 1024 / NT;  // at most 1024 threads per SM: 64 registers each would be too few
+  static constexpr int CTAS_PER_SM = CTAS_SMEM < 1 ? 1 : (CTAS_SMEM < CTAS_THREADS ? CTAS_SMEM : (CTAS_THREADS < 1 ? 1 : CTAS_THREADS));
 };
 
 // rows of the local lattice: r = x1 + L1 (x2 + L2 x3); site of (r, x0) = r L0 + x0
@@ -82,12 +95,12 @@ static __global__ void links4_transpose_kernel(cd* __restrict__ Ut, const cd* __
 // SECOND = false:  out = D in                         (sweep 1)
 // SECOND = true :  out = (m2 + sigma) p0 - D in       (sweep 2; in = D p0) [+ partial Gram p0^dag out per CTA]
 // rows [row_begin, row_end) of the local lattice; b rows per tile (b L0 G <= NTC).
-template <int N, bool SECOND, bool GRAM>
-__global__ void __launch_bounds__(Dirac4TileGeom<N>::NT, 1)
+template <int N, int NCW_, int NSMAX, bool SECOND, bool GRAM>
+__global__ void __launch_bounds__((Dirac4TileGeom<N, NCW_, NSMAX>::NT), (Dirac4TileGeom<N, NCW_, NSMAX>::CTAS_PER_SM))
 dirac4_tile_kernel(const cd* __restrict__ in, const cd* __restrict__ p0, cd* __restrict__ out, const cd* __restrict__ Ut,
                    Rows4 geo, long long row_begin, long long row_end, int b, double m2, double sigma,
                    cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl) {
-  using Geo = Dirac4TileGeom<N>;
+  using Geo = Dirac4TileGeom<N, NCW_, NSMAX>;
   constexpr int R = Geo::R, G = Geo::G, SITE = Geo::SITE, NS = Geo::NSTAGE, NTC = Geo::NTC;
   constexpr int NDIR = SECOND ? 8 : 7;  // stages per tile: own rows (both x0 directions), 1+, 1-, 2+, 2-, 3+, 3-, [p0]
   if (ctrl != nullptr && (ctrl->done | ctrl->stop)) return;
@@ -103,7 +116,7 @@ dirac4_tile_kernel(const cd* __restrict__ in, const cd* __restrict__ p0, cd* __r
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, NTC);
+      mbar_init(empty + s, Geo::NCW);  // one arrival per compute warp (256 single arrivals would serialise on the barrier word)
     }
     mbar_fence_init();
   }
@@ -189,7 +202,8 @@ dirac4_tile_kernel(const cd* __restrict__ in, const cd* __restrict__ p0, cd* __r
             apply_link_dag_sub<R>(sU + ls * 9, v, acc);
         }
       }
-      mbar_arrive(empty + st);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(empty + st);
     }
     // ---- the result tile: through shared memory, one bulk store ----
     if (tid == 0 && store_pending) bulk_wait_read0();  // the previous tile's store has drained sOut
@@ -230,7 +244,10 @@ dirac4_tile_kernel(const cd* __restrict__ in, const cd* __restrict__ p0, cd* __r
     }
     store_pending = true;
     if (GRAM) gram.accumulate(sP, sOut, 3 * ns);  // P^dag T over the rows of this tile
-    if (SECOND) mbar_arrive(empty + st_p0);
+    if (SECOND) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(empty + st_p0);
+    }
   }
   if (tid == 0) bulk_wait0();
   if (GRAM) {

@@ -273,12 +273,14 @@ struct Ops {
         cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)APG::SMEM_BYTES);
     }
-    if constexpr (D4::OK) {
-      cudaFuncSetAttribute(dirac4_tile_kernel<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D4::SMEM_BYTES);
-      cudaFuncSetAttribute(dirac4_tile_kernel<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D4::SMEM_BYTES);
-      if constexpr (D4::CAN_GRAM)
-        cudaFuncSetAttribute(dirac4_tile_kernel<N, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D4::SMEM_BYTES);
-    }
+    dirac4_tile_prepare<2>();
+    dirac4_tile_prepare<3>();
+    dirac4_tile_prepare<4>();
+    dirac4_tile_prepare<6>();
+    dirac4_tile_prepare<8>();
+    dirac4_tile_prepare<12>();
+    dirac4_tile_prepare<16>();
+    dirac4_tile_prepare<24>();
     if constexpr (CHAIN) {
       if constexpr (DFMA_GRAM)
         cudaFuncSetAttribute(dirac_chain_kernel<N, CG_, CK, CW, CGMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -348,33 +350,80 @@ struct Ops {
     return err();
   }
 
-  using D4 = Dirac4TileGeom<N>;
+  // Shapes of the tiled 4-D sweep compiled in: NCW compute warps, a two-stage ring, as many CTAs per SM as fit.
+  // Measured (24^4, N = 12, profiles/r02_4d_tile_shapes.jsonl): many small CTAs beat one large one with a deep ring
+  // -- 3 warps x 4 CTAs 331 us, 6 warps x 2 CTAs 397 us, 6 warps x 1 CTA with four stages 518 us -- the sweep waits
+  // for row deliveries, and independent pipelines hide that better than depth.  So: the smallest shape whose tile
+  // holds one lattice row.
+  using D4 = Dirac4TileGeom<N, 3, 2>;  // what the shapes share: R, G, SITE
+  template <int NCW>
+  static int dirac4_tile_launch(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* Ut, const Rows4& geo,
+                                long long row_begin, long long row_end, double m2, double sigma, int second, cd* gpart,
+                                const Ctrl* ctrl, int sms) {
+    using Geo = Dirac4TileGeom<N, NCW, 2>;
+    if constexpr (Geo::OK) {
+      if (gpart != nullptr && !Geo::CAN_GRAM) return -static_cast<int>(cudaErrorNotSupported);
+      const int b = Geo::NTC / (Geo::G * geo.L0);  // rows per tile
+      const long long ntiles = (row_end - row_begin + b - 1) / b;
+      const int grid = clamp_grid(ntiles, Geo::CTAS_PER_SM * sms);   // persistent CTAs, as many as are resident
+      if (!second)
+        dirac4_tile_kernel<N, NCW, 2, false, false><<<grid, Geo::NT, Geo::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end,
+                                                                                            b, m2, sigma, nullptr, ctrl);
+      else if (gpart == nullptr)
+        dirac4_tile_kernel<N, NCW, 2, true, false><<<grid, Geo::NT, Geo::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end,
+                                                                                           b, m2, sigma, nullptr, ctrl);
+      else if constexpr (Geo::CAN_GRAM)
+        dirac4_tile_kernel<N, NCW, 2, true, true><<<grid, Geo::NT, Geo::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end,
+                                                                                          b, m2, sigma, gpart, ctrl);
+      return grid;
+    }
+    return -static_cast<int>(cudaErrorNotSupported);
+  }
+  template <int NCW>
+  static void dirac4_tile_prepare() {
+    using Geo = Dirac4TileGeom<N, NCW, 2>;
+    if constexpr (Geo::OK) {
+      cudaFuncSetAttribute(dirac4_tile_kernel<N, NCW, 2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo::SMEM_BYTES);
+      cudaFuncSetAttribute(dirac4_tile_kernel<N, NCW, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo::SMEM_BYTES);
+      if constexpr (Geo::CAN_GRAM)
+        cudaFuncSetAttribute(dirac4_tile_kernel<N, NCW, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo::SMEM_BYTES);
+    }
+  }
+  template <int NCW>
+  static bool dirac4_fits(int L0) {  // a row of L0 sites fits the tile of this shape
+    using Geo = Dirac4TileGeom<N, NCW, 2>;
+    return Geo::OK && static_cast<long long>(L0) * Geo::G <= Geo::NTC;
+  }
   static int dirac4_tile(cudaStream_t st, const cd* in, const cd* p0, cd* out, const cd* Ut, const Lattice4* lat,
                          long long site_stride_mu, long long row_begin, long long row_end, double m2, double sigma, int second,
                          cd* gpart, const Ctrl* ctrl, int sms, int* launches) {
-    if constexpr (D4::OK) {
-      if (row_end <= row_begin) return 0;
-      if (static_cast<long long>(lat->L0) * D4::G > D4::NTC) return -static_cast<int>(cudaErrorNotSupported);
-      if (gpart != nullptr && (!D4::CAN_GRAM || !second)) return -static_cast<int>(cudaErrorNotSupported);
-      prepare(sms);
-      const int b = D4::NTC / (D4::G * lat->L0);  // rows per tile
-      const long long ntiles = (row_end - row_begin + b - 1) / b;
-      const int grid = clamp_grid(ntiles, sms);   // one persistent CTA per SM
-      const Rows4 geo = {lat->L0, lat->L1, lat->L2, lat->L3, site_stride_mu};
-      if (!second)
-        dirac4_tile_kernel<N, false, false><<<grid, D4::NT, D4::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end, b, m2,
-                                                                                   sigma, nullptr, ctrl);
-      else if (gpart == nullptr)
-        dirac4_tile_kernel<N, true, false><<<grid, D4::NT, D4::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end, b, m2,
-                                                                                  sigma, nullptr, ctrl);
-      else if constexpr (D4::CAN_GRAM)
-        dirac4_tile_kernel<N, true, true><<<grid, D4::NT, D4::SMEM_BYTES, st>>>(in, p0, out, Ut, geo, row_begin, row_end, b, m2,
-                                                                                 sigma, gpart, ctrl);
-      if (launches) ++*launches;
-      const int e = err();
-      return e ? e : (gpart != nullptr ? grid : 0);
+    if (row_end <= row_begin) return 0;
+    if (gpart != nullptr && !second) return -static_cast<int>(cudaErrorNotSupported);
+    const int L0 = lat->L0;
+    // BCG_DIRAC4_WARPS = 2 / 3 / 4 / 6 / 8 / 12 / 16 / 24 forces a shape (if the row fits it)
+    static const int forced = [] { const char* e = std::getenv("BCG_DIRAC4_WARPS"); return e ? std::atoi(e) : 0; }();
+    const int cand[8] = {2, 3, 4, 6, 8, 12, 16, 24};
+    const bool fits[8] = {dirac4_fits<2>(L0), dirac4_fits<3>(L0), dirac4_fits<4>(L0), dirac4_fits<6>(L0),
+                          dirac4_fits<8>(L0), dirac4_fits<12>(L0), dirac4_fits<16>(L0), dirac4_fits<24>(L0)};
+    int best = -1;
+    for (int i = 7; i >= 0; --i)
+      if (fits[i]) best = i;
+    for (int i = 0; i < 8; ++i)
+      if (forced == cand[i] && fits[i]) best = i;
+    if (best < 0) return -static_cast<int>(cudaErrorNotSupported);
+    prepare(sms);
+    const Rows4 geo = {lat->L0, lat->L1, lat->L2, lat->L3, site_stride_mu};
+    int grid = 0;
+#define BCG_D4_CASE(W) case W: grid = dirac4_tile_launch<W>(st, in, p0, out, Ut, geo, row_begin, row_end, m2, sigma, second, gpart, ctrl, sms); break;
+    switch (cand[best]) {
+      BCG_D4_CASE(2) BCG_D4_CASE(3) BCG_D4_CASE(4) BCG_D4_CASE(6) BCG_D4_CASE(8) BCG_D4_CASE(12) BCG_D4_CASE(16)
+      default: grid = dirac4_tile_launch<24>(st, in, p0, out, Ut, geo, row_begin, row_end, m2, sigma, second, gpart, ctrl, sms); break;
     }
-    return -static_cast<int>(cudaErrorNotSupported);
+#undef BCG_D4_CASE
+    if (grid < 0) return grid;  // this shape cannot fuse the Gram at this N: the caller runs the plain sweep + the Gram kernel
+    if (launches) ++*launches;
+    const int e = err();
+    return e ? e : (gpart != nullptr ? grid : 0);
   }
 
   static int gram(cudaStream_t st, const cd* A, const cd* B, long long V, cd* gpart, const Ctrl* ctrl, int sms,
@@ -689,7 +738,7 @@ const OpsTable* make_ops() {
                              &Ops<N>::dirac,
                              &Ops<N>::dirac_v1,
                              &Ops<N>::dirac4_sweep,
-                             Ops<N>::D4::OK ? &Ops<N>::dirac4_tile : nullptr,
+                             &Ops<N>::dirac4_tile,
                              &Ops<N>::gram,
                              &Ops<N>::axpy_gram,
                              Ops<N>::APIPE ? 1 : 0,
