@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = [("shift_pair_kernel", "shift_pair"), ("shift_dmma_kernel", "shift_dmma_pair"), ("shift_pipe_kernel", "shift_update"),
+NAMES = [("shift_stag_kernel", "shift_stag4"), ("shift_pair_kernel", "shift_pair"), ("shift_dmma_kernel", "shift_dmma_pair"), ("shift_pipe_kernel", "shift_update"),
          ("axpy_pipe_kernel", "axpy_gram"), ("dirac_chain_kernel", "dirac_gram")]
 wname, reps = sys.argv[1], sys.argv[2:]
 inst = {}
