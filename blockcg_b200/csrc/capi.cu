@@ -953,10 +953,10 @@ namespace {
 
 // Schedule of the multishift update (build_shift_items in common.cuh): BCG_PAIR = 0 plain, 1 alternating,
 // 2 staggered (default where the kernels support it).
-// Default: 3 (every fourth iteration) from kDeepDeferralMinSites sites per rank on -- measured 3 % faster than
-// schedule 2 at 24^4 and 8 % slower at 41 k sites, where the launch's fixed costs count
-// (profiles/r02_ab_shift_depth_and_overlap.jsonl).
-constexpr long long kDeepDeferralMinSites = 250000;
+// Default: 3 (every fourth iteration) from kDeepDeferralMinSites sites per rank on -- measured against schedule 2:
+// 6 % faster at 24^4 (full solve), 4 % at 166 k sites (one and two ranks), 1 % slower at 83 k and 8 % at 41 k sites,
+// where the launch's fixed costs count (profiles/r02_ab_shift_depth_and_overlap.jsonl).
+constexpr long long kDeepDeferralMinSites = 120000;
 int pair_default(const bcg_ctx* c) {  // read per solve, so that a test can compare the schedules in one process
   const char* e = std::getenv("BCG_PAIR");
   if (e) return std::atoi(e);

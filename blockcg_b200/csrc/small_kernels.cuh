@@ -79,7 +79,9 @@ __device__ __noinline__ void sm_identity(cd* dst, int N) {
   }
   __syncthreads();
 }
-// C = A*B ; C must not alias A or B
+// C = A*B ; C must not alias A or B.  (A fully unrolled body for the compile-time sizes 4 / 8 / 12 / 16 was measured
+// SLOWER than this loop, 0.3-0.5 us per kernel: these kernels run once per iteration, and straight-line code is
+// fetched once where a loop body is fetched once and reused -- profiles/r02_ab_coefficient_kernels.jsonl.)
 __device__ __noinline__ void sm_mm(cd* C, const cd* A, const cd* B, int N) {
   for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
     BCG_IJ(e, i, j);
@@ -201,6 +203,20 @@ __device__ __noinline__ void sm_reduce_gram(cd* G, const cd* __restrict__ gpart,
   __syncthreads();
 }
 
+// One entry of column step k.  A warp holds entries of all three kinds (column k, trailing block, untouched),
+// so the cases are evaluated without branches and selected: a divergent warp would walk through the three
+// dependent chains one after the other, and these kernels are nothing but latency.  Every entry's arithmetic
+// is that of its own case, unchanged.
+__device__ __forceinline__ cd chol_entry(const cd* src, int N, int e, int i, int j, int k, double x, double r, double r2) {
+  const cd v = src[e];
+  const cd aik = src[i + N * k], ajk = src[j + N * k];
+  cd upd = v;
+  cmsub(upd, cscale(aik, r2), cconj(ajk));
+  const cd col = (i == k) ? cmake(x * r, 0.0) : cscale(v, r);
+  const bool active = i >= j && j >= k;
+  return active ? (j == k ? col : upd) : v;
+}
+
 // Cholesky of the Hermitian G (real diagonal + lower triangle are read, as Eigen LLT.h:301-328),
 // returned as R = L^dag (upper, exactly zero below the diagonal), as fields.hpp:142.  Returns -1 or
 // the index of the first non-positive pivot (uniform across the CTA).  Lw: N*N scratch.
@@ -210,6 +226,15 @@ __device__ __noinline__ void sm_reduce_gram(cd* G, const cd* __restrict__ gpart,
 // (Eigen's unblocked LLT is left-looking: same factor, sums associated differently.)
 __device__ __noinline__ int sm_chol_upper(cd* R, const cd* G, cd* Lw, int N, int* s_info) {
   const int nn = N * N;
+  // one entry per thread (the shape the coefficient kernels are launched with): (i, j) stay in registers
+  const bool one = nn <= static_cast<int>(blockDim.x);
+  const int e0 = threadIdx.x;
+  int i0 = 0, j0 = 0;
+  if (one && e0 < nn) {
+    BCG_IJ(e0, i, j);
+    i0 = i;
+    j0 = j;
+  }
   sm_copy(Lw, G, nn);
   cd* src = Lw;
   cd* dst = R;
@@ -221,18 +246,13 @@ __device__ __noinline__ int sm_chol_upper(cd* R, const cd* G, cd* Lw, int N, int
       break;
     }
     const double r = rsqrt(x), r2 = r * r;
-    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-      BCG_IJ(e, i, j);
-      cd v = src[e];
-      if (i >= j && j >= k) {
-        if (j == k) {
-          v = (i == k) ? cmake(x * r, 0.0) : cscale(v, r);
-        } else {
-          const cd aik = src[i + N * k], ajk = src[j + N * k];
-          cmsub(v, cscale(aik, r2), cconj(ajk));
-        }
+    if (one) {
+      if (e0 < nn) dst[e0] = chol_entry(src, N, e0, i0, j0, k, x, r, r2);
+    } else {
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+        BCG_IJ(e, i, j);
+        dst[e] = chol_entry(src, N, e, i, j, k, x, r, r2);
       }
-      dst[e] = v;
     }
     __syncthreads();
     cd* t = src;
@@ -401,9 +421,27 @@ __device__ __forceinline__ void sm_lu_solve(cd* X, cd* lu, const LuWork& w, int 
 // The elimination ping-pongs between A and the scratch matrix W (one barrier per column);
 // every warp finds the pivot row itself (16 candidates per shuffle tree, no hand-off).
 // PIVOT = false takes the diagonal entry (Hermitian positive definite input).
+// One entry of elimination step k (pivot row br, rp = 1 / pivot), branch-free for the same reason as chol_entry:
+// pivot row, pivot column and the rest are three dependent chains that a divergent warp would run in turn.
+__device__ __forceinline__ cd gj_entry(const cd* src, int N, int i, int j, int k, int br, cd rp) {
+  const int si = (i == k) ? br : (i == br) ? k : i;  // source row after the exchange k <-> br
+  const cd ask = src[si + N * k], abj = src[br + N * j], asj = src[si + N * j];
+  cd rest = asj;
+  cmsub(rest, cmul(ask, rp), abj);
+  const cd row = cmul(abj, rp);
+  const cd col = cmul(cmake(-ask.x, -ask.y), rp);
+  return (i == k) ? ((j == k) ? rp : row) : ((j == k) ? col : rest);
+}
 template <bool PIVOT>
 __device__ __noinline__ void sm_inverse(cd* A, cd* W, int N, int* piv, int* s_info) {
   const int tid = threadIdx.x, lane = tid & 31, nn = N * N;
+  const bool one = nn <= static_cast<int>(blockDim.x);  // one entry per thread: (i, j) stay in registers
+  int i0 = 0, j0 = 0;
+  if (one && tid < nn) {
+    BCG_IJ(tid, i, j);
+    i0 = i;
+    j0 = j;
+  }
   if (tid == 0) *s_info = -1;
   cd* src = A;
   cd* dst = W;
@@ -429,20 +467,13 @@ __device__ __noinline__ void sm_inverse(cd* A, cd* W, int N, int* piv, int* s_in
     if (tid == 0 && !(pa > 0.0)) *s_info = k;
     const double pn = __drcp_rn(pa);
     const cd rp = cmake(pk.x * pn, -pk.y * pn);  // 1 / pivot
-    for (int e = tid; e < nn; e += blockDim.x) {
-      BCG_IJ(e, i, j);
-      const int si = (i == k) ? br : (i == br) ? k : i;  // source row after the exchange k <-> br
-      cd v;
-      if (i == k) {
-        v = (j == k) ? rp : cmul(src[br + N * j], rp);
-      } else if (j == k) {
-        const cd aik = src[si + N * k];
-        v = cmul(cmake(-aik.x, -aik.y), rp);
-      } else {
-        v = src[si + N * j];
-        cmsub(v, cmul(src[si + N * k], rp), src[br + N * j]);
+    if (one) {
+      if (tid < nn) dst[tid] = gj_entry(src, N, i0, j0, k, br, rp);
+    } else {
+      for (int e = tid; e < nn; e += blockDim.x) {
+        BCG_IJ(e, i, j);
+        dst[e] = gj_entry(src, N, i, j, k, br, rp);
       }
-      dst[e] = v;
     }
     __syncthreads();
     cd* t = src;
@@ -605,8 +636,17 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
                  Ctrl* __restrict__ ctrl, const GramWait gw) {
   pdl_wait();
   pdl_trigger();
-  if (ctrl->done) return;
-  if (ctrl->stop) {
+  // Everything the prologue needs from the control block in ONE round trip to L2 (the loads are independent and
+  // issued before the first branch): these kernels are chains of latencies, and a dependent global load is ~1/3 us.
+  const int c_done = ctrl->done, c_stop = ctrl->stop;
+  const int iter = ctrl->iter_b + 1;
+  const int n_unconv_old = ctrl->n_unconv_b;
+  unsigned conv_mask = 0u;
+#pragma unroll
+  for (int q = 1; q < kMaxShifts; ++q) conv_mask |= (ctrl->conv[q] != 0 ? 1u : 0u) << q;
+  const unsigned long long seq_base = gw.nranks ? ctrl->seq_base : 0ull;
+  if (c_done) return;
+  if (c_stop) {
     __syncthreads();
     if (threadIdx.x == 0) ctrl->done = 1;
     return;
@@ -614,18 +654,33 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   const int sh = blockIdx.x;
   extern __shared__ __align__(16) unsigned char raw[];
   const int N = L.N, nn = N * N;
-  SmallSmem s;
-  s.carve(raw, N);
-  sm_init_ij(N);
-  const int iter = ctrl->iter_b + 1;
-  const int n_unconv_old = ctrl->n_unconv_b;
   // shifts that passed the test in the previous iteration were still updated in it and drop out
   // from this one on (block_solvers.hpp:161,175-181): every passing shift decrements the count,
   // which always retires the highest index.
   int n_unconv = n_unconv_old;
   for (int q = 1; q < n_unconv_old; ++q)
-    if (ctrl->conv[q]) --n_unconv;
+    if ((conv_mask >> q) & 1u) --n_unconv;
   if (sh >= n_unconv && sh > 0) return;
+  // the operands of the second half of this kernel, fetched now (one entry per thread) so that their latency
+  // hides behind the Gram wait and the first inverse; all of them were written by earlier kernels
+  const bool one = nn <= static_cast<int>(blockDim.x);
+  const bool own = one && static_cast<int>(threadIdx.x) < nn;
+  const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
+  const cd* ainv_old_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1);
+  const double sig_s = ctrl->sigma[sh], sig_0 = ctrl->sigma[0];
+  cd pre0 = czero(), pre1 = czero(), pre2 = czero();
+  if (own) {
+    if (sh == 0) {
+      pre0 = mats[L.fixed(M_DELTA) + threadIdx.x];
+    } else {
+      pre0 = rho_old_g[threadIdx.x];
+      pre1 = ainv_old_g[threadIdx.x];
+      pre2 = mats[L.beta_s(sh) + threadIdx.x];
+    }
+  }
+  SmallSmem s;
+  s.carve(raw, N);
+  sm_init_ij(N);
   if (sh == 0 && threadIdx.x == 0) {
     ctrl->iter = iter;
     ctrl->n_unconv = n_unconv;
@@ -635,7 +690,7 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   cd* alpha = s.mat[2];
   const cd* gsrc = gpart;
   int nsrc = nparts;
-  if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
+  if (!sm_wait_peers(gw, seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
   sm_reduce_gram(Ainv, gsrc, nsrc, N, s.mat[4]);
   sm_copy(alpha, Ainv, nn);
   sm_inverse<false>(alpha, lu, N, s.lw.rt, s.info);  // alpha = (P0^dag T)^-1, Hermitian positive definite
@@ -646,7 +701,12 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
       ctrl->status = 3;
       ctrl->stop = 1;
     }
-    sm_copy(delta, mats + L.fixed(M_DELTA), nn);
+    if (one) {
+      if (own) delta[threadIdx.x] = pre0;
+      __syncthreads();
+    } else {
+      sm_copy(delta, mats + L.fixed(M_DELTA), nn);
+    }
     sm_mm(ad, alpha, delta, N);
     cd* ainv_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0);
     for (int e = threadIdx.x; e < nn; e += blockDim.x) {
@@ -664,11 +724,18 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   cd* t1 = s.mat[7];
   cd* t2 = s.mat[8];
   cd* G = s.mat[0];  // Ainv is not needed any more: scratch
-  const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
-  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    rho_old[e] = rho_old_g[e];
-    ainv_old[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1) + e];
-    beta[e] = mats[L.beta_s(sh) + e];
+  if (one) {
+    if (own) {
+      rho_old[threadIdx.x] = pre0;
+      ainv_old[threadIdx.x] = pre1;
+      beta[threadIdx.x] = pre2;
+    }
+  } else {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      rho_old[e] = rho_old_g[e];
+      ainv_old[e] = ainv_old_g[e];
+      beta[e] = mats[L.beta_s(sh) + e];
+    }
   }
   __syncthreads();
   // beta_s_inv = I + (sigma_s - sigma_0) alpha + alpha rho_old alpha_inv_old (I - beta_s) rho_old^dag
@@ -681,7 +748,7 @@ rq_step_a_kernel(cd* __restrict__ mats, MatLayout L, const cd* __restrict__ gpar
   __syncthreads();
   sm_mm(G, t2, t1, N);
   sm_mm_adj(t1, G, rho_old, N);  // ... * rho_old^dag
-  const double ds = ctrl->sigma[sh] - ctrl->sigma[0];
+  const double ds = sig_s - sig_0;
   for (int e = threadIdx.x; e < nn; e += blockDim.x) {
     const double id = ((g_ij[e] & 0xffff) == (g_ij[e] >> 16)) ? 1.0 : 0.0;
     lu[e] = cmake((id + ds * alpha[e].x) + t1[e].x, (ds * alpha[e].y) + t1[e].y);
@@ -702,28 +769,55 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
                  const cd* __restrict__ gpart, int nparts, Ctrl* __restrict__ ctrl, const GramWait gw) {
   pdl_wait();
   pdl_trigger();
-  if (ctrl->done) return;
+  // the control block in one round trip, the operands of the second half fetched before the Gram wait (see the A-step)
+  const int c_done = ctrl->done, c_n_unconv = ctrl->n_unconv, iter = ctrl->iter;
+  const unsigned long long seq_base = gw.nranks ? ctrl->seq_base : 0ull;
+  if (c_done) return;
   const int sh = blockIdx.x;
-  if (sh >= ctrl->n_unconv) return;
+  if (sh >= c_n_unconv) return;
   extern __shared__ __align__(16) unsigned char raw[];
   const int N = L.N, nn = N * N;
+  const bool one = nn <= static_cast<int>(blockDim.x);
+  const bool own = one && static_cast<int>(threadIdx.x) < nn;
+  const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
+  const cd* ainv_old_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1);
+  const cd* ainv_g = mats + L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0);
+  cd pre[6];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) pre[t] = czero();
+  if (own) {
+    if (sh == 0) {
+      pre[0] = mats[L.fixed(M_DELTA) + threadIdx.x];
+    } else {
+      pre[0] = mats[L.fixed(M_ALPHA) + threadIdx.x];
+      pre[1] = rho_old_g[threadIdx.x];
+      pre[2] = ainv_old_g[threadIdx.x];
+      pre[3] = ainv_g[threadIdx.x];
+      pre[4] = mats[L.beta_s(sh) + threadIdx.x];  // this iteration's beta_s, from the A-step
+      pre[5] = mats[L.alpha_s(sh) + threadIdx.x];
+    }
+  }
   SmallSmem s;
   s.carve(raw, N);
   sm_init_ij(N);
-  const int iter = ctrl->iter;
   cd* G = s.mat[0];
   cd* rho = s.mat[1];
   cd* t0 = s.mat[2];
   const cd* gsrc = gpart;
   int nsrc = nparts;
-  if (!sm_wait_peers(gw, ctrl->seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
+  if (!sm_wait_peers(gw, seq_base + static_cast<unsigned long long>(iter), nn, gsrc, nsrc, ctrl)) return;
   sm_reduce_gram(G, gsrc, nsrc, N, s.mat[4]);
   const int info = sm_chol_upper(rho, G, t0, N, s.info);
   cd* rho_g = mats + L.fixed((iter & 1) ? M_RHO1 : M_RHO0);
   if (sh == 0) {
     cd* delta = s.mat[3];
     cd* dn = s.mat[4];
-    sm_copy(delta, mats + L.fixed(M_DELTA), nn);
+    if (one) {
+      if (own) delta[threadIdx.x] = pre[0];
+      __syncthreads();
+    } else {
+      sm_copy(delta, mats + L.fixed(M_DELTA), nn);
+    }
     sm_mm(dn, rho, delta, N);
     sm_rownorms(s.vec, dn, N);
     for (int e = threadIdx.x; e < nn; e += blockDim.x) {
@@ -796,14 +890,24 @@ rq_step_b_kernel(cd* __restrict__ mats, MatLayout L, const double* __restrict__ 
   cd* t2 = s.mat[8];
   cd* as = s.mat[9];
   cd* ainv = s.mat[10];
-  const cd* rho_old_g = mats + L.fixed((iter & 1) ? M_RHO0 : M_RHO1);
-  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    alpha[e] = mats[L.fixed(M_ALPHA) + e];
-    rho_old[e] = rho_old_g[e];
-    ainv_old[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV0 : M_ALPHA_INV1) + e];
-    ainv[e] = mats[L.fixed((iter & 1) ? M_ALPHA_INV1 : M_ALPHA_INV0) + e];
-    beta[e] = mats[L.beta_s(sh) + e];  // this iteration's beta_s, from the A-step
-    as[e] = mats[L.alpha_s(sh) + e];
+  if (one) {
+    if (own) {
+      alpha[threadIdx.x] = pre[0];
+      rho_old[threadIdx.x] = pre[1];
+      ainv_old[threadIdx.x] = pre[2];
+      ainv[threadIdx.x] = pre[3];
+      beta[threadIdx.x] = pre[4];
+      as[threadIdx.x] = pre[5];
+    }
+  } else {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      alpha[e] = mats[L.fixed(M_ALPHA) + e];
+      rho_old[e] = rho_old_g[e];
+      ainv_old[e] = ainv_old_g[e];
+      ainv[e] = ainv_g[e];
+      beta[e] = mats[L.beta_s(sh) + e];  // this iteration's beta_s, from the A-step
+      as[e] = mats[L.alpha_s(sh) + e];
+    }
   }
   __syncthreads();
   // alpha_s = beta_s alpha rho_old alpha_inv_old alpha_s  (left to right)
