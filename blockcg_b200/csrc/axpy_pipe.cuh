@@ -37,9 +37,81 @@ struct AxpyPipeGeom {
   static constexpr int TILE = (TS / 2) * PAIR;       // complex per staged field tile
   static constexpr int NSTAGE = 4;
   static constexpr int STAGE = 2 * TILE;             // T tile, Q tile
-  static constexpr size_t SMEM_BYTES = sizeof(cd) * (NSTAGE * STAGE + N * N) + 8 * 4 * NSTAGE + 16;
+  static constexpr size_t BASE_BYTES = sizeof(cd) * (NSTAGE * STAGE + N * N) + 8 * 4 * NSTAGE + 16;
+  // folded A-step (AlphaFold): three N x N work matrices + the slices of the rank-order sum of the peer blocks
+  static constexpr int FOLD_ELEMS = 3 * N * N + 8 * (N * (N + 1) / 2);
+  static constexpr bool FOLD_OK = BASE_BYTES + sizeof(cd) * FOLD_ELEMS + 1024 <= 227 * 1024 && N * N <= NT;
+  static constexpr size_t SMEM_BYTES = BASE_BYTES + (FOLD_OK ? sizeof(cd) * FOLD_ELEMS : 0);
   static constexpr int ROWS = 3 * TS;
 };
+
+// alpha = (P0^dag T)^-1 in the prologue of the Q update, exactly as the A-step forms it (small_kernels.cuh:
+// sm_reduce_gram, sm_inverse<false> -- the same sums in the same order, the same elimination entry by entry), one
+// matrix entry per thread.  w: FOLD_ELEMS complex of scratch; on return w[N*N ..] or w[2 N*N ..] (the returned
+// pointer) holds alpha.  Every thread of the CTA must call it (CTA barriers inside).
+template <int N>
+__device__ __noinline__ const cd* fold_alpha(cd* w, const cd* __restrict__ gsrc, int nsrc, int step_threads) {
+  constexpr int nn = N * N, E = N * (N + 1) / 2;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  cd* G = w;
+  cd* A = w + nn;
+  cd* W = w + 2 * nn;
+  cd* slices = w + 3 * nn;
+  const int i = tid % N, j = tid / N;  // this thread's entry (tid < nn)
+  if (nsrc == 1) {  // already reduced by the stencil: lower triangle + conjugate mirror (fields.hpp:103-122)
+    if (tid < nn) A[tid] = (i >= j) ? gsrc[tid] : cconj(gsrc[j + N * i]);
+    __syncthreads();
+  } else {
+    // the blocks of the ranks summed in rank order, sliced as the A-step's own threads slice it (sm_reduce_gram)
+    int nsl = step_threads / E;
+    nsl = nsl < 1 ? 1 : (nsl > 8 ? 8 : nsl);
+    for (int wk = tid; wk < E * nsl; wk += nthr) {
+      const int t = wk % E, q = wk / E;
+      int jj = 0, rest = t;
+      while (rest >= N - jj) {
+        rest -= N - jj;
+        ++jj;
+      }
+      const int e = (jj + rest) + N * jj;
+      double re = 0.0, im = 0.0;
+      for (int p = q; p < nsrc; p += nsl) {
+        const cd a = gsrc[static_cast<size_t>(p) * nn + e];
+        re += a.x;
+        im += a.y;
+      }
+      slices[wk] = cmake(re, im);
+    }
+    __syncthreads();
+    for (int t = tid; t < E; t += nthr) {
+      int jj = 0, rest = t;
+      while (rest >= N - jj) {
+        rest -= N - jj;
+        ++jj;
+      }
+      const int ii = jj + rest;
+      cd sum = slices[t];
+      for (int q = 1; q < nsl; ++q) sum = cadd(sum, slices[q * E + t]);
+      A[ii + N * jj] = sum;
+      if (ii != jj) A[jj + N * ii] = cconj(sum);
+    }
+    __syncthreads();
+  }
+  (void)G;
+  cd* src = A;
+  cd* dst = W;
+#pragma unroll 1
+  for (int k = 0; k < N; ++k) {  // Gauss-Jordan, no pivoting (Hermitian positive definite): sm_inverse<false>
+    const cd pk = src[k + N * k];
+    const double pn = __drcp_rn(cabs2(pk));
+    const cd rp = cmake(pk.x * pn, -pk.y * pn);
+    if (tid < nn) dst[tid] = gj_entry(src, N, i, j, k, k, rp);
+    __syncthreads();
+    cd* t = src;
+    src = dst;
+    dst = t;
+  }
+  return src;
+}
 
 // GRAM: 0 none, 1 four Gram warps with DFMA (GramPart), 2 the same warps on the FP64 tensor instruction (GramDmma)
 template <int N, int TS, int GRAM>
@@ -47,7 +119,7 @@ __global__ void __launch_bounds__(AxpyPipeGeom<N, TS>::NT, 1)
 axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQout,
                  const __grid_constant__ CUtensorMap tmT,
                  const cd* __restrict__ M, long long V, cd* __restrict__ gpart, const Ctrl* __restrict__ ctrl,
-                 const GramPeers peers, int reverse) {
+                 const GramPeers peers, int reverse, const AlphaFold fold) {
   // reverse != 0: tiles are visited from the high end of the field down.  The stencil that ran
   // just before wrote T from site 0 upwards, so the top ~100 MB of T are still in L2; and the
   // multishift update that runs next reads Q from site 0 upwards, i.e. the part written last.
@@ -56,7 +128,9 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   constexpr int PAIR = Geo::PAIR, TILE = Geo::TILE, STAGE = Geo::STAGE, NS = Geo::NSTAGE;
   pdl_wait();
   pdl_trigger();
-  if (ctrl != nullptr && ctrl->done) return;
+  // fold.on: M = -alpha is formed here, from the stencil's Gram, and the A-step runs beside this kernel -- so `done`
+  // (which that A-step sets after the last iteration) may not be up yet: `stop` says the same one iteration earlier
+  if (ctrl != nullptr && (ctrl->done | (fold.on ? ctrl->stop : 0))) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* sbuf = reinterpret_cast<cd*>(smem_raw);
@@ -76,13 +150,6 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     mbar_fence_init();
   }
-  // coefficient matrix, column groups interleaved: element (k, j) at (k*JC + j%JC)*NSPLIT + j/JC
-  for (int e = tid; e < N * N; e += Geo::NT) {
-    const int k = e % N, j = e / N;
-    sM[(k * JC + (j % JC)) * NSPLIT + j / JC] = M[e];
-  }
-  __syncthreads();
-
   const long long ntiles = (V + TS - 1) / TS;
   const int nmine = static_cast<int>(blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   auto tile_pair0 = [&](int i) {  // first site pair of this CTA's i-th tile
@@ -90,10 +157,64 @@ axpy_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     return static_cast<int>((reverse ? ntiles - 1 - tidx : tidx) * (TS / 2));
   };
   constexpr uint32_t TILE_BYTES = TILE * sizeof(cd);
+  int preloaded = 0;  // tiles the loader lane has requested before the folded A-step
+
+  bool folded = false;
+  if constexpr (Geo::FOLD_OK) {
+    if (fold.on) {
+      folded = true;
+      __syncthreads();  // barriers initialised
+      if (warp == Geo::WARP_LOAD && lane == 0) {  // the first tiles travel while alpha is being formed
+        for (; preloaded < nmine && preloaded < NS; ++preloaded) {
+          mbar_arrive_expect_tx(full + preloaded, 2 * TILE_BYTES);
+          tma_load_2d(sbuf + preloaded * STAGE, &tmT, 0, tile_pair0(preloaded), full + preloaded);
+          tma_load_2d(sbuf + preloaded * STAGE + TILE, &tmQ, 0, tile_pair0(preloaded), full + preloaded);
+        }
+      }
+      cd* w = reinterpret_cast<cd*>(smem_raw + ((Geo::BASE_BYTES + 15) / 16) * 16);
+      const cd* gsrc = fold.gsrc;
+      int nsrc = fold.nsrc;
+      if (fold.gw.nranks > 0) {  // slab decomposition: every rank's block of this iteration has to have landed
+        __shared__ int timed_out;
+        if (tid == 0) timed_out = 0;
+        __syncthreads();
+        const unsigned long long kseq = ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter_b + 1);
+        if (tid < fold.gw.nranks) {
+          const long long t0 = clock64();
+          while (ld_acquire_sys(fold.gw.seq + tid) < kseq)
+            if (clock64() - t0 > kSpinTimeoutClocks) {  // the A-step beside this kernel reports it
+              timed_out = 1;
+              break;
+            }
+        }
+        __syncthreads();
+        if (timed_out) {
+          if (warp == Geo::WARP_LOAD && lane == 0)
+            for (int i = 0; i < preloaded; ++i) mbar_wait(full + i, 0u);  // no copy may outlive the CTA
+          return;
+        }
+        gsrc = fold.gw.slots + static_cast<size_t>(kseq & 1ull) * fold.gw.nranks * (N * N);
+        nsrc = fold.gw.nranks;
+      }
+      const cd* alpha = fold_alpha<N>(w, gsrc, nsrc, fold.step_threads);
+      for (int e = tid; e < N * N; e += Geo::NT) {
+        const int k = e % N, j = e / N;
+        sM[(k * JC + (j % JC)) * NSPLIT + j / JC] = cmake(-alpha[e].x, -alpha[e].y);
+      }
+    }
+  }
+  if (!folded) {
+    // coefficient matrix, column groups interleaved: element (k, j) at (k*JC + j%JC)*NSPLIT + j/JC
+    for (int e = tid; e < N * N; e += Geo::NT) {
+      const int k = e % N, j = e / N;
+      sM[(k * JC + (j % JC)) * NSPLIT + j / JC] = M[e];
+    }
+  }
+  __syncthreads();
 
   if (warp == Geo::WARP_LOAD) {
     if (lane != 0) return;
-    for (int i = 0; i < nmine; ++i) {
+    for (int i = preloaded; i < nmine; ++i) {
       const int st = i % NS;
       if (i >= NS) {  // stage free: Gram and store of the tile that used it are done
         const uint32_t par = static_cast<uint32_t>((i / NS - 1) & 1);

@@ -591,6 +591,9 @@ static int ctx_create(bcg_ctx** out, int64_t v_local, const int64_t* dims, int n
     const int b = static_cast<int>(c->small_smem);
     CU(cudaFuncSetAttribute(rq_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CU(cudaFuncSetAttribute(rq_step_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    // runs beside the Q update (AlphaFold): same carve-out as that kernel, so that the two can share an SM
+    CU(cudaFuncSetAttribute(rq_step_a_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            (int)cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(rq_step_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CU(cudaFuncSetAttribute(bcg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
     CU(cudaFuncSetAttribute(bcg_step_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
@@ -969,6 +972,14 @@ bool dmma_default() {  // read per solve, so that a test can compare both paths 
   return e ? std::atoi(e) != 0 : true;
 }
 
+// The A-step off the critical path (AlphaFold, axpy_pipe.cuh).  BCG_FOLD_A=0 restores the serial chain.
+bool fold_a_default() {
+  const char* e = std::getenv("BCG_FOLD_A");
+  const char* v1 = std::getenv("BCG_FORCE_V1");
+  if (v1 && (std::atoi(v1) & 2)) return false;
+  return e ? std::atoi(e) != 0 : true;
+}
+
 bool fold_halo_default() {
   const char* e = std::getenv("BCG_FOLD_HALO");
   return e ? std::atoi(e) != 0 : true;
@@ -997,6 +1008,7 @@ struct LoopPlan {
   bool dmma;  // (S)BCGrQ update by shift_dmma_kernel (plain or paired schedule)
   int nthr;   // threads of the coefficient kernels
   bool fold_halo;  // the update kernel refreshes the halo of P0 itself (no halo kernel in the loop)
+  bool fold_a;     // (S)BCGrQ: the Q update forms alpha itself (AlphaFold); the A-step runs beside it on c->stream2
   cd* P0;
   cd* T;
   cd* Q;  // BCG: R
@@ -1069,7 +1081,14 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
     return BCG_OK;
   }
   BCG_MARK(1);
-  if (p.kind == 1)
+  if (p.fold_a) {
+    // fork: the A-step (alpha for the B-step, A_0, beta_s) runs on the second stream beside the Q update, which forms
+    // its own alpha; joined before the B-step
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    launch_pdl(rq_step_a_kernel, p.n_shifts, p.nthr, c->small_smem, c->stream2, c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
+    CU(cudaEventRecord(c->ev_join, c->stream2));
+  } else if (p.kind == 1)
     launch_pdl(rq_step_a_kernel, p.n_shifts, p.nthr, c->small_smem, c->stream, c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
   else
     bcg_step_a_kernel<<<1, kSmallThreads, c->small_smem, c->stream>>>(c->mats, c->L, gsrc, nsrc, c->ctrl, gw0);
@@ -1083,9 +1102,23 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
   // overlapped launch of two iterations ago: it reads the Q field this update overwrites, the operand sets and the
   // snapshot slot this iteration's B-step overwrites
   if (p.overlap && rel >= 2) CU(cudaStreamWaitEvent(c->stream, c->ev_bulk[(pos + 1) & 1], 0));
-  np = c->ops->axpy_gram(c->stream, Qin, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches,
-                         fused ? &gp1 : nullptr, Qout);
-  KL(np);
+  if (p.fold_a) {
+    AlphaFold af;
+    std::memset(&af, 0, sizeof af);
+    af.gsrc = gsrc;
+    af.nsrc = nsrc;
+    af.gw = gw0;
+    af.step_threads = p.nthr;
+    af.on = 1;
+    np = c->ops->axpy_gram_fold(c->stream, Qin, p.T, c->V, c->gpart, c->ctrl, c->sms, launches, fused ? &gp1 : nullptr, Qout,
+                                &af);
+    KL(np);
+    CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join: the B-step needs alpha, alpha^-1, beta_s
+  } else {
+    np = c->ops->axpy_gram(c->stream, Qin, p.T, mat(c, M_NEGALPHA), c->V, c->gpart, c->ctrl, c->sms, launches,
+                           fused ? &gp1 : nullptr, Qout);
+    KL(np);
+  }
   r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
   if (r) return r;
   BCG_MARK(3);
@@ -1172,7 +1205,7 @@ int run_loop(bcg_ctx* c, const LoopPlan& p, bcg_solve_info* info, int64_t* launc
   key.push_back(p.pair ? &c->work_Qp : nullptr);
   key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(((p.bulk_ctas * 2 + (p.overlap ? 1 : 0)) * 8 + p.ring) * 64 + p.pair * 16 + p.depth)));
   key.push_back(p.dmma ? &c->work_Q : nullptr);
-  key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(p.nthr * 2 + (p.fold_halo ? 1 : 0))));
+  key.push_back(reinterpret_cast<const void*>(static_cast<uintptr_t>(p.nthr * 4 + (p.fold_a ? 2 : 0) + (p.fold_halo ? 1 : 0))));
   GraphCache& g = c->graph;
   if (!g.exec || g.kind != p.kind || g.n_shifts != p.n_shifts || g.batch != batch || g.key != key) {
     if (g.exec) {
@@ -1377,6 +1410,8 @@ int solve_rq(bcg_ctx* c, const int* xh, int b, const double* sigma, int n_shifts
   // and the next stencil waits for them and unpacks them itself (needs the parity-chain stencil: N = 4, 8, 12, 16).
   p.fold_halo = dmma && c->ndim == 1 && c->V >= 4 && c->V % 2 == 0 && fold_halo_default() &&
                 (c->nranks == 1 || (c->p2p_ready && c->ops->fused_exchange));
+  // the A-step beside the Q update: the reference's 1-D chain only (the 4-D apply uses the second stream itself)
+  p.fold_a = c->ndim == 1 && c->ops->axpy_gram_fold != nullptr && fold_a_default();
   p.depth = depth;
   p.ring = ring;
   p.overlap = overlap;

@@ -296,6 +296,8 @@ struct GramPeers {                      // one of the two Gram channels (0: P^da
   unsigned long long* seq[kMaxRanks];   // rank r's sequence words: [nranks]
   int nranks;                           // 0 = no exchange (one rank, or the NCCL path of the primitives)
   int rank;
+  int iter_from_b;                      // channel 1 only: take the iteration number from ctrl->iter_b + 1 (the A-step, which
+                                        // writes ctrl->iter, runs BESIDE the producing kernel: AlphaFold)
 };
 struct HaloPeers {
   cd* lo_of_right;                      // right neighbour's "from the left" slots: [2 parities][2 sites]
@@ -320,6 +322,28 @@ struct GramWait {                       // consumer side of a Gram channel
   const unsigned long long* seq;        // this rank's sequence words: [nranks]
   int nranks;                           // 0 = plain mode (blocks handed over in stream order)
 };
+// The A-step folded into the Q update (axpy_pipe.cuh): every CTA of `Q' = Q - T alpha` forms alpha = (P0^dag T)^-1
+// itself in its prologue, from the Gram block(s) the stencil left behind, while its first tiles are in flight; the
+// A-step kernel (which still produces alpha for the B-step, A_0 and the beta_s) leaves the critical path and runs on
+// a second stream beside the Q update.  Same functions of the same data in the same order: the same bits.
+struct AlphaFold {
+  const cd* gsrc;      // reduced Gram block (nsrc == 1) or, with gw.nranks > 0, taken from the peer slots
+  int nsrc;
+  GramWait gw;
+  int step_threads;    // threads of the A-step kernel: its rank-order sum of the peer blocks is sliced by that number
+  int on;
+};
+// One entry of elimination step k of the Gauss-Jordan inverse (pivot row br, rp = 1 / pivot), branch-free: pivot
+// row, pivot column and the rest are three dependent chains that a divergent warp would run in turn.
+__device__ __forceinline__ cd gj_entry(const cd* src, int N, int i, int j, int k, int br, cd rp) {
+  const int si = (i == k) ? br : (i == br) ? k : i;  // source row after the exchange k <-> br
+  const cd ask = src[si + N * k], abj = src[br + N * j], asj = src[si + N * j];
+  cd rest = asj;
+  cmsub(rest, cmul(ask, rp), abj);
+  const cd row = cmul(abj, rp);
+  const cd col = cmul(cmake(-ask.x, -ask.y), rp);
+  return (i == k) ? ((j == k) ? rp : row) : ((j == k) ? col : rest);
+}
 constexpr long long kSpinTimeoutClocks = 20000000000LL;  // ~10 s: a peer that never arrives is an error, not a hang
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

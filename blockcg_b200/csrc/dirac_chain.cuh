@@ -249,8 +249,10 @@ __device__ __noinline__ void gram_group_reduce(cd* __restrict__ gbuf, int gram_w
   if (s_old != static_cast<unsigned>(ngroups - 1)) return;
   __threadfence();
   // ---- ... and the last group: add the group sums in group order, publish ----
-  const unsigned long long k =
-      (ctrl != nullptr) ? ctrl->seq_base + static_cast<unsigned long long>(ctrl->iter + (channel == 0 ? 1 : 0)) : 0ull;
+  // iteration number of this Gram: the A-step increments ctrl->iter between the two channels; with the A-step running
+  // beside the Q update (AlphaFold) channel 1 derives it from the previous B-step's copy instead
+  const int it_now = (ctrl == nullptr) ? 0 : (channel == 0 ? ctrl->iter + 1 : (peers.iter_from_b ? ctrl->iter_b + 1 : ctrl->iter));
+  const unsigned long long k = (ctrl != nullptr) ? ctrl->seq_base + static_cast<unsigned long long>(it_now) : 0ull;
   const int np = (ctrl != nullptr) ? peers.nranks : 0;
   constexpr int CH = 20;  // group sums fetched per round (148 SMs / 8 = 19 groups: one round)
 #pragma unroll 1

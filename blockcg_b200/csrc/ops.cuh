@@ -83,6 +83,10 @@ struct OpsTable {
   // tensor-map views of the chain stencil are rectangular and reach past the end of the field
   long long (*field_capacity)(long long V, int sms);
   void (*prepare)(int sms);  // occupancy queries / smem opt-in; call once outside stream capture
+  // axpy_gram with M = -alpha formed in the kernel's prologue from the stencil's Gram (AlphaFold, axpy_pipe.cuh): the
+  // A-step kernel need not have run.  nullptr where the pipelined kernel is not built or the scratch does not fit.
+  int (*axpy_gram_fold)(cudaStream_t st, cd* Q, const cd* T, long long V, cd* gpart, const Ctrl* ctrl, int sms,
+                        int* launches, const GramPeers* peers, cd* Qout, const AlphaFold* fold);
 };
 
 const OpsTable* get_ops(int N);  // nullptr if N is not compiled in
@@ -269,9 +273,14 @@ struct Ops {
                              (int)APG::SMEM_BYTES);
       cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)APG::SMEM_BYTES);
-      if constexpr (N % 4 == 0)
+      if constexpr (N % 4 == 0) {
         cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)APG::SMEM_BYTES);
+        // the A-step kernel runs BESIDE this one (AlphaFold): ask for the largest shared-memory carve-out, so that an SM
+        // configured for this kernel's CTA still has room for a coefficient CTA (and vice versa)
+        cudaFuncSetAttribute(axpy_pipe_kernel<N, APIPE_TS, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
+      }
     }
     dirac4_tile_prepare<2>();
     dirac4_tile_prepare<3>();
@@ -497,10 +506,28 @@ struct Ops {
     return 0;
   }
 
+  static constexpr bool AFOLD = APIPE && APG::FOLD_OK;
+  static int axpy_gram_fold(cudaStream_t st, cd* Q, const cd* T, long long V, cd* gpart, const Ctrl* ctrl, int sms,
+                            int* launches, const GramPeers* peers, cd* Qout, const AlphaFold* fold) {
+    if (!AFOLD || fold == nullptr || !fold->on || gpart == nullptr || ctrl == nullptr || (force_v1() & 2))
+      return -static_cast<int>(cudaErrorNotSupported);
+    return axpy_gram_impl(st, Q, T, nullptr, V, gpart, ctrl, sms, launches, peers, Qout, fold);
+  }
   static int axpy_gram(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
                        const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers, cd* Qout) {
+    return axpy_gram_impl(st, Q, T, M, V, gpart, ctrl, sms, launches, peers, Qout, nullptr);
+  }
+  static int axpy_gram_impl(cudaStream_t st, cd* Q, const cd* T, const cd* M, long long V, cd* gpart,
+                            const Ctrl* ctrl, int sms, int* launches, const GramPeers* peers, cd* Qout,
+                            const AlphaFold* fold) {
     GramPeers pe;
     if (peers) pe = *peers; else std::memset(&pe, 0, sizeof pe);
+    AlphaFold af;
+    std::memset(&af, 0, sizeof af);
+    if (fold) {
+      af = *fold;
+      pe.iter_from_b = 1;  // the A-step (which writes ctrl->iter) runs beside this kernel
+    }
     if constexpr (!APIPE) {
       if (Qout != nullptr && Qout != Q) return -static_cast<int>(cudaErrorNotSupported);
     }
@@ -517,16 +544,16 @@ struct Ops {
         bool done = false;
         if constexpr (N % 4 == 0) {
           if (gram_dmma() || !DFMA_GRAM) {
-            launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 2>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+            launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 2>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse(), af);
             done = true;
           }
         }
         if constexpr (DFMA_GRAM) {
           if (!done)
-            launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 1>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse());
+            launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 1>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, gpart, ctrl, pe, axpy_reverse(), af);
         }
       } else {
-        launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 0>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, static_cast<cd*>(nullptr), ctrl, pe, axpy_reverse());
+        launch_pdl(axpy_pipe_kernel<N, APIPE_TS, 0>, grid, APG::NT, APG::SMEM_BYTES, st, tmQ, tmQo, tmT, M, V, static_cast<cd*>(nullptr), ctrl, pe, axpy_reverse(), af);
       }
       if (launches) ++*launches;
       e = err();
@@ -753,7 +780,8 @@ const OpsTable* make_ops() {
                              Ops<N>::STAG_OK ? &Ops<N>::shift_update_stag : nullptr,
                              &Ops<N>::max_partials,
                              &Ops<N>::field_capacity,
-                             &Ops<N>::prepare};
+                             &Ops<N>::prepare,
+                             Ops<N>::AFOLD ? &Ops<N>::axpy_gram_fold : nullptr};
   return &t;
 }
 #endif  // BCG_N

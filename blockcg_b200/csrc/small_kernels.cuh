@@ -421,17 +421,7 @@ __device__ __forceinline__ void sm_lu_solve(cd* X, cd* lu, const LuWork& w, int 
 // The elimination ping-pongs between A and the scratch matrix W (one barrier per column);
 // every warp finds the pivot row itself (16 candidates per shuffle tree, no hand-off).
 // PIVOT = false takes the diagonal entry (Hermitian positive definite input).
-// One entry of elimination step k (pivot row br, rp = 1 / pivot), branch-free for the same reason as chol_entry:
-// pivot row, pivot column and the rest are three dependent chains that a divergent warp would run in turn.
-__device__ __forceinline__ cd gj_entry(const cd* src, int N, int i, int j, int k, int br, cd rp) {
-  const int si = (i == k) ? br : (i == br) ? k : i;  // source row after the exchange k <-> br
-  const cd ask = src[si + N * k], abj = src[br + N * j], asj = src[si + N * j];
-  cd rest = asj;
-  cmsub(rest, cmul(ask, rp), abj);
-  const cd row = cmul(abj, rp);
-  const cd col = cmul(cmake(-ask.x, -ask.y), rp);
-  return (i == k) ? ((j == k) ? rp : row) : ((j == k) ? col : rest);
-}
+// (one entry of an elimination step: gj_entry in common.cuh, shared with the folded A-step of axpy_pipe.cuh)
 template <bool PIVOT>
 __device__ __noinline__ void sm_inverse(cd* A, cd* W, int N, int* piv, int* s_info) {
   const int tid = threadIdx.x, lane = tid & 31, nn = N * N;
