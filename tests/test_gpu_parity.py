@@ -330,9 +330,11 @@ def test_paired_multishift_update_is_bit_identical(bcg, oracle, V, N, max_it, ep
     modes = {"0": {"BCG_PAIR": "0"}, "1": {"BCG_PAIR": "1"}, "2": {"BCG_PAIR": "2"},
              "3/3": {"BCG_PAIR": "3", "BCG_DEPTH": "3"}, "3/4": {"BCG_PAIR": "3", "BCG_DEPTH": "4"},
              "3/2/overlap": {"BCG_PAIR": "3", "BCG_DEPTH": "2", "BCG_OVERLAP": "1"},
-             "3/3/overlap": {"BCG_PAIR": "3", "BCG_DEPTH": "3", "BCG_OVERLAP": "1", "BCG_BULK_CTAS": "37"}}
+             "3/3/overlap": {"BCG_PAIR": "3", "BCG_DEPTH": "3", "BCG_OVERLAP": "1", "BCG_BULK_CTAS": "37"},
+             # the serial chain K1 -> A-step -> K3 against the default (K3 forms alpha itself, the A-step runs beside it)
+             "2/serial-A": {"BCG_PAIR": "2", "BCG_FOLD_A": "0"}, "3/4/serial-A": {"BCG_PAIR": "3", "BCG_DEPTH": "4", "BCG_FOLD_A": "0"}}
     for mode, env in modes.items():
-        for k in ("BCG_PAIR", "BCG_DEPTH", "BCG_OVERLAP", "BCG_BULK_CTAS"):
+        for k in ("BCG_PAIR", "BCG_DEPTH", "BCG_OVERLAP", "BCG_BULK_CTAS", "BCG_FOLD_A"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
