@@ -129,6 +129,10 @@ struct bcg_ctx {
   cd* gpart = nullptr;
   size_t gpart_elems = 0;
   cd* gred = nullptr;  // reduced Gram (multi-rank path / primitives): N*N
+  // Gram buffers of the Q update when the A-step runs beside it (AlphaFold): that kernel still reads the stencil's
+  // block from gpart / gred while the Q update's epilogue writes its own
+  cd* gpart_q = nullptr;
+  cd* gred_q = nullptr;
   cd* mats = nullptr;
   MatLayout L{};
   double* b_norm = nullptr;
@@ -313,19 +317,24 @@ int halo_refresh(bcg_ctx* c, cd* f, int site, const Ctrl* ctrl, int* launches) {
 // partials themselves (reduced in fixed order inside the coefficient kernel).
 // Multi rank: reduce locally, all-reduce the N x N block over NVLink, hand the
 // kernels one "partial".
-int gram_finalize(bcg_ctx* c, int nparts, const cd** src, int* nsrc, int* launches, bool fused_exchange = false) {
+// second_set: the partial blocks are in c->gpart_q and the reduced block goes to c->gred_q (the Q update's Gram
+// while the A-step, which runs beside that kernel, may still be reading the stencil's from the first set)
+int gram_finalize(bcg_ctx* c, int nparts, const cd** src, int* nsrc, int* launches, bool fused_exchange = false,
+                  bool second_set = false) {
+  cd* gpart = second_set ? c->gpart_q : c->gpart;
+  cd* gred = second_set ? c->gred_q : c->gred;
   if (c->nranks == 1 || fused_exchange) {  // fused_exchange: the producing kernel has pushed the block to all peers
-    *src = c->gpart;
+    *src = gpart;
     *nsrc = nparts;
     return BCG_OK;
   }
   if (!c->comm_ready) return fail(c, BCG_ERR_NO_COMM, "multi-rank context: call bcg_comm_init first");
   const size_t nn = c->L.nn();
-  gram_reduce_kernel<<<1, kSmallThreads, (1 + kRedSlices) * nn * sizeof(cd), c->stream>>>(c->gred, c->gpart, nparts, c->N);
+  gram_reduce_kernel<<<1, kSmallThreads, (1 + kRedSlices) * nn * sizeof(cd), c->stream>>>(gred, gpart, nparts, c->N);
   if (launches) ++*launches;
   CU(cudaGetLastError());
-  NC(ncclAllReduce(c->gred, c->gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
-  *src = c->gred;
+  NC(ncclAllReduce(gred, gred, 2 * nn, ncclDouble, ncclSum, c->comm, c->stream));
+  *src = gred;
   *nsrc = 1;
   return BCG_OK;
 }
@@ -568,6 +577,9 @@ static int ctx_create(bcg_ctx** out, int64_t v_local, const int64_t* dims, int n
   CU(cudaMalloc(&c->gpart, c->gpart_elems * sizeof(cd)));
   CU(cudaMemset(c->gpart, 0, c->gpart_elems * sizeof(cd)));  // arrival counters of gram_group_reduce start at zero
   CU(cudaMalloc(&c->gred, c->L.nn() * sizeof(cd)));
+  CU(cudaMalloc(&c->gpart_q, c->gpart_elems * sizeof(cd)));
+  CU(cudaMemset(c->gpart_q, 0, c->gpart_elems * sizeof(cd)));
+  CU(cudaMalloc(&c->gred_q, c->L.nn() * sizeof(cd)));
   CU(cudaMalloc(&c->mats, c->L.total() * sizeof(cd)));
   CU(cudaMemset(c->mats, 0, c->L.total() * sizeof(cd)));
   CU(cudaMalloc(&c->b_norm, sizeof(double) * n_rhs));
@@ -630,6 +642,8 @@ int bcg_ctx_destroy(bcg_ctx* c) {
   cudaFree(c->Ut_alloc);
   cudaFree(c->gpart);
   cudaFree(c->gred);
+  cudaFree(c->gpart_q);
+  cudaFree(c->gred_q);
   cudaFree(c->mats);
   cudaFree(c->b_norm);
   cudaFree(c->ctrl);
@@ -1110,7 +1124,8 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
     af.gw = gw0;
     af.step_threads = p.nthr;
     af.on = 1;
-    np = c->ops->axpy_gram_fold(c->stream, Qin, p.T, c->V, c->gpart, c->ctrl, c->sms, launches, fused ? &gp1 : nullptr, Qout,
+    // its Gram goes to the second set of buffers: the A-step beside it reads the stencil's block from the first
+    np = c->ops->axpy_gram_fold(c->stream, Qin, p.T, c->V, c->gpart_q, c->ctrl, c->sms, launches, fused ? &gp1 : nullptr, Qout,
                                 &af);
     KL(np);
     CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join: the B-step needs alpha, alpha^-1, beta_s
@@ -1119,7 +1134,7 @@ int enqueue_iteration(bcg_ctx* c, const LoopPlan& p, int* launches, cudaEvent_t*
                            fused ? &gp1 : nullptr, Qout);
     KL(np);
   }
-  r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused);
+  r = gram_finalize(c, np, &gsrc, &nsrc, launches, fused, p.fold_a);
   if (r) return r;
   BCG_MARK(3);
   if (p.kind == 1)
