@@ -595,6 +595,22 @@ def run_ours(args, w, wname):
                 "note": "numerator = fixed per-unit bytes of SURVEY 8(d) (2F per back-substitution + 4F per system update) x "
                         "units per launch, so fusing / pairing shows as bandwidth; moved_* = bytes the launches really moved "
                         "(device-side count); traffic = ncu dram bytes of an all-systems-active launch (profiles/)"}
+    # The update kernel is bound by the FP64 (tensor-instruction) pipe rather than by HBM since the deferred schedules
+    # (ncu: profiles/r02_ncu_full_top3_depth4.txt), so the same launch is also put against the FP64 peak measured on
+    # B200 by tools/micro/fp64_pipes.cu (DFMA 35.5, DMMA 36.8 TFLOP/s on the same pipe).  Real flops of the complex
+    # arithmetic: a system update is two N x N products per site and colour (2 * 3 * N^2 complex multiply-adds of
+    # 8 flops), the back-substitution 3 * N(N+1)/2 of them.
+    try:
+        w_act = sum(n * max(a, 1) for a, n in enumerate(hist)) / n_it
+        flops_launch = 8.0 * Vl * (3.0 * N * (N + 1) / 2 + 6.0 * N * N * w_act)
+        fp64_peak = 35.5
+        roofline["fp64"] = {"achieved": flops_launch / w_ms / 1e9, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": flops_launch / w_ms / 1e9 / fp64_peak,
+                            "peak_source": "tools/micro/fp64_pipes.cu on B200 (DFMA issue rate; DMMA shares the pipe), DESIGN.md 4",
+                            "note": "complex-arithmetic flops of the histogram-weighted launch / its time; the kernel's ncu "
+                                    "figures with all systems active: DMMA pipe 63 %, DRAM 42 %"}
+    except Exception:   # explanatory key only: never let it take the bench line down
+        pass
     dirac = kern["dirac_gram"]
 
     if rank != 0:
