@@ -38,8 +38,8 @@ struct AxpyPipeGeom {
   static constexpr int NSTAGE = 4;
   static constexpr int STAGE = 2 * TILE;             // T tile, Q tile
   static constexpr size_t BASE_BYTES = sizeof(cd) * (NSTAGE * STAGE + N * N) + 8 * 4 * NSTAGE + 16;
-  // folded A-step (AlphaFold): three N x N work matrices + the slices of the rank-order sum of the peer blocks
-  static constexpr int FOLD_ELEMS = 3 * N * N + 8 * (N * (N + 1) / 2);
+  // folded A-step (AlphaFold): two N x N work matrices + the slices of the rank-order sum of the peer blocks
+  static constexpr int FOLD_ELEMS = 2 * N * N + 8 * (N * (N + 1) / 2);
   static constexpr bool FOLD_OK = BASE_BYTES + sizeof(cd) * FOLD_ELEMS + 1024 <= 227 * 1024 && N * N <= NT;
   static constexpr size_t SMEM_BYTES = BASE_BYTES + (FOLD_OK ? sizeof(cd) * FOLD_ELEMS : 0);
   static constexpr int ROWS = 3 * TS;
@@ -47,16 +47,15 @@ struct AxpyPipeGeom {
 
 // alpha = (P0^dag T)^-1 in the prologue of the Q update, exactly as the A-step forms it (small_kernels.cuh:
 // sm_reduce_gram, sm_inverse<false> -- the same sums in the same order, the same elimination entry by entry), one
-// matrix entry per thread.  w: FOLD_ELEMS complex of scratch; on return w[N*N ..] or w[2 N*N ..] (the returned
-// pointer) holds alpha.  Every thread of the CTA must call it (CTA barriers inside).
+// matrix entry per thread.  w: FOLD_ELEMS complex of scratch; the returned pointer (one of the two work matrices)
+// holds alpha.  Every thread of the CTA must call it (CTA barriers inside).
 template <int N>
 __device__ __noinline__ const cd* fold_alpha(cd* w, const cd* __restrict__ gsrc, int nsrc, int step_threads) {
   constexpr int nn = N * N, E = N * (N + 1) / 2;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  cd* G = w;
-  cd* A = w + nn;
-  cd* W = w + 2 * nn;
-  cd* slices = w + 3 * nn;
+  cd* A = w;
+  cd* W = w + nn;
+  cd* slices = w + 2 * nn;
   const int i = tid % N, j = tid / N;  // this thread's entry (tid < nn)
   if (nsrc == 1) {  // already reduced by the stencil: lower triangle + conjugate mirror (fields.hpp:103-122)
     if (tid < nn) A[tid] = (i >= j) ? gsrc[tid] : cconj(gsrc[j + N * i]);
@@ -96,7 +95,6 @@ __device__ __noinline__ const cd* fold_alpha(cd* w, const cd* __restrict__ gsrc,
     }
     __syncthreads();
   }
-  (void)G;
   cd* src = A;
   cd* dst = W;
 #pragma unroll 1
