@@ -271,12 +271,12 @@ EXCHANGE = ("halo sites and Gram blocks exchanged by P2P stores over NVLink from
 
 
 def config_of(wname, w, gpus):
-    nf = 2 * len(w["shifts"]) + 3
+    nf = 2 * len(w["shifts"]) + 3   # X_s, P_s, Q, Q', T (the deep deferral keeps up to two more Q fields)
     return {"workload": wname, "solver": w["solver"], "V": w["V"], "n_rhs": w["N"], "n_shifts": len(w["shifts"]),
             "mass": w["mass"], "eps": w["eps"], "eps_shifts": w["eps_shifts"],
             "operator": "reference 1-D chain (inc/dirac_op.hpp:13-21)",
             "partition": "1 slab" if gpus == 1 else "%d contiguous site slabs; %s" % (gpus, EXCHANGE),
-            "l2_policy": ("%d fields of %.0f MB each per GPU stream through every pair of iterations (working set %s"
+            "l2_policy": ("at least %d fields of %.0f MB each per GPU stream through every group of 2-4 iterations (working set %s"
                           " the 126 MB L2); no explicit flush"
                           % (nf, 48.0 * w["N"] * w["V"] / gpus / 1e6,
                              "exceeds" if nf * 48.0 * w["N"] * w["V"] / gpus > 126e6 else "FITS IN"))}
