@@ -197,3 +197,18 @@ def test_deep_staggered_schedule_applies_every_update_once_and_in_order():
                 ring[i % R] = act[i - 1]
             assert got == want, (depth, overlap, S, act, got, want)
             assert total <= plain + depth * n_it
+
+
+def test_every_diagnostic_switch_is_documented():
+    """Every environment switch the library reads (getenv("BCG_...") in csrc/) has a row in INTEGRATION.md."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, "blockcg_b200", "csrc", "*.cu*")):
+        names.update(re.findall(r'getenv\("(BCG_[A-Z0-9_]+)"\)', open(f).read()))
+    assert names, "no switches found: the pattern is stale"
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
+
